@@ -1,0 +1,407 @@
+// c_abi.cpp -- the extern "C" boundary declared in include/spmv_b200.h.
+// Thin, exception-safe adapters over the C++ surface: the C structs are
+// layout-identical to the C++ ones (asserted below), by-value results become
+// out-parameters, and anything thrown is turned into a status code.
+#include "spmv_b200.h"
+
+#include "internal.hpp"
+
+#include <cstring>
+#include <new>
+
+using namespace spmv;
+
+// ---- layout identity between the two surfaces ---------------------------------
+static_assert(sizeof(spmv_b200_csr) == sizeof(CSRMatrix) && offsetof(spmv_b200_csr, d_row_ptrs) == offsetof(CSRMatrix, d_row_ptrs) &&
+              offsetof(spmv_b200_csr, owns_device_memory) == offsetof(CSRMatrix, owns_device_memory), "csr");
+static_assert(sizeof(spmv_b200_ell) == sizeof(ELLMatrix) && offsetof(spmv_b200_ell, d_col_indices) == offsetof(ELLMatrix, d_col_indices) &&
+              offsetof(spmv_b200_ell, owns_device_memory) == offsetof(ELLMatrix, owns_device_memory), "ell");
+static_assert(sizeof(spmv_b200_config) == sizeof(SpMVConfig) && offsetof(spmv_b200_config, use_texture) == offsetof(SpMVConfig, use_texture), "config");
+static_assert(sizeof(spmv_b200_result) == sizeof(SpMVResult) && offsetof(spmv_b200_result, error_code) == offsetof(SpMVResult, error_code), "result");
+static_assert(sizeof(spmv_b200_csr_stats) == sizeof(CSRStats), "stats");
+static_assert(sizeof(spmv_b200_bandwidth) == sizeof(BandwidthMetrics), "bandwidth");
+static_assert(sizeof(spmv_b200_pagerank_config) == sizeof(PageRankConfig), "pagerank config");
+static_assert(sizeof(spmv_b200_pagerank_result) == sizeof(PageRankResult) && offsetof(spmv_b200_pagerank_result, converged) == offsetof(PageRankResult, converged), "pagerank result");
+static_assert(sizeof(spmv_b200_topk_node) == sizeof(TopKNode), "topk");
+static_assert(sizeof(spmv_b200_bench_config) == sizeof(BenchmarkConfig), "bench config");
+
+namespace {
+
+inline CSRMatrix* cpp(spmv_b200_csr* m) { return reinterpret_cast<CSRMatrix*>(m); }
+inline const CSRMatrix* cpp(const spmv_b200_csr* m) { return reinterpret_cast<const CSRMatrix*>(m); }
+inline ELLMatrix* cpp(spmv_b200_ell* m) { return reinterpret_cast<ELLMatrix*>(m); }
+inline const ELLMatrix* cpp(const spmv_b200_ell* m) { return reinterpret_cast<const ELLMatrix*>(m); }
+inline const SpMVConfig* cpp(const spmv_b200_config* c) { return reinterpret_cast<const SpMVConfig*>(c); }
+inline const PageRankConfig* cpp(const spmv_b200_pagerank_config* c) { return reinterpret_cast<const PageRankConfig*>(c); }
+inline const BenchmarkConfig* cpp(const spmv_b200_bench_config* c) { return reinterpret_cast<const BenchmarkConfig*>(c); }
+
+constexpr int kBadArg = SPMV_B200_INVALID_ARGUMENT;
+
+int status_of(const std::exception* e) {
+    if (dynamic_cast<const std::bad_alloc*>(e)) return SPMV_B200_OUT_OF_MEMORY;
+    if (dynamic_cast<const CudaException*>(e)) return SPMV_B200_CUDA_MALLOC;
+    return SPMV_B200_INVALID_ARGUMENT;
+}
+
+// Runs fn(), mapping exceptions to a status.
+template <typename Fn>
+int guarded(Fn fn) {
+    try {
+        return fn();
+    } catch (const std::exception& e) {
+        return status_of(&e);
+    } catch (...) {
+        return SPMV_B200_INVALID_ARGUMENT;
+    }
+}
+
+void to_c(const SpMVResult& r, spmv_b200_result* out) {
+    if (!out) return;
+    out->y = r.y;
+    out->elapsed_ms = r.elapsed_ms;
+    out->gflops = r.gflops;
+    out->bandwidth_gb_s = r.bandwidth_gb_s;
+    out->error_code = r.error_code;
+}
+
+void to_c(const BenchmarkResult& r, spmv_b200_bench_result* out) {
+    if (!out) return;
+    std::memset(out, 0, sizeof(*out));
+    std::strncpy(out->name, r.name.c_str(), sizeof(out->name) - 1);
+    out->execution_time_ms = r.execution_time_ms;
+    out->gflops = r.gflops;
+    out->bandwidth_gb_s = r.bandwidth_gb_s;
+    out->avg_time_ms = r.avg_time_ms;
+    out->min_time_ms = r.min_time_ms;
+    out->max_time_ms = r.max_time_ms;
+    out->stddev_time_ms = r.stddev_time_ms;
+    out->num_runs = r.num_runs;
+}
+
+BenchmarkResult from_c(const spmv_b200_bench_result* in) {
+    BenchmarkResult r;
+    r.name.assign(in->name, strnlen(in->name, sizeof(in->name)));
+    r.execution_time_ms = in->execution_time_ms;
+    r.gflops = in->gflops;
+    r.bandwidth_gb_s = in->bandwidth_gb_s;
+    r.avg_time_ms = in->avg_time_ms;
+    r.min_time_ms = in->min_time_ms;
+    r.max_time_ms = in->max_time_ms;
+    r.stddev_time_ms = in->stddev_time_ms;
+    r.num_runs = in->num_runs;
+    return r;
+}
+
+void to_c(const BandwidthMetrics& m, spmv_b200_bandwidth* out) {
+    out->theoretical_bandwidth_gb_s = m.theoretical_bandwidth_gb_s;
+    out->achieved_bandwidth_gb_s = m.achieved_bandwidth_gb_s;
+    out->efficiency = m.efficiency;
+}
+
+void to_c(const SpMVConfig& c, spmv_b200_config* out) {
+    out->kernel_type = static_cast<int>(c.kernel_type);
+    out->block_size = c.block_size;
+    out->use_texture = c.use_texture;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* spmv_b200_error_string(int status) { return spmv_error_string(static_cast<SpMVError>(status)); }
+const char* spmv_b200_version(void) { return "spmv_b200 0.1 (sm_100a)"; }
+unsigned long long spmv_b200_launch_count(void) { return b200::launch_count(); }
+
+// ---- A. CSR ---------------------------------------------------------------------
+spmv_b200_csr* spmv_b200_csr_create(int rows, int cols, int nnz) {
+    try { return reinterpret_cast<spmv_b200_csr*>(csr_create(rows, cols, nnz)); } catch (...) { return nullptr; }
+}
+void spmv_b200_csr_destroy(spmv_b200_csr* m) { csr_destroy(cpp(m)); }
+int spmv_b200_csr_from_dense(spmv_b200_csr* m, const float* dense, int rows, int cols) {
+    return guarded([&] { return csr_from_dense(cpp(m), dense, rows, cols); });
+}
+int spmv_b200_csr_to_dense(const spmv_b200_csr* m, float* dense) { return guarded([&] { return csr_to_dense(cpp(m), dense); }); }
+float spmv_b200_csr_get_element(const spmv_b200_csr* m, int row, int col) { return csr_get_element(cpp(m), row, col); }
+int spmv_b200_csr_to_gpu(spmv_b200_csr* m) { return guarded([&] { return csr_to_gpu(cpp(m)); }); }
+int spmv_b200_csr_from_gpu(spmv_b200_csr* m) { return guarded([&] { return csr_from_gpu(cpp(m)); }); }
+void spmv_b200_csr_free_gpu(spmv_b200_csr* m) { csr_free_gpu(cpp(m)); }
+int spmv_b200_csr_serialize(const spmv_b200_csr* m, const char* f) { return guarded([&] { return csr_serialize(cpp(m), f); }); }
+int spmv_b200_csr_deserialize(spmv_b200_csr* m, const char* f) { return guarded([&] { return csr_deserialize(cpp(m), f); }); }
+int spmv_b200_csr_compute_stats(const spmv_b200_csr* m, spmv_b200_csr_stats* out) {
+    if (!out) return kBadArg;
+    const CSRStats s = csr_compute_stats(cpp(m));
+    out->avg_nnz_per_row = s.avg_nnz_per_row;
+    out->max_nnz_per_row = s.max_nnz_per_row;
+    out->min_nnz_per_row = s.min_nnz_per_row;
+    out->skewness = s.skewness;
+    return 0;
+}
+
+// ---- B. ELL ---------------------------------------------------------------------
+spmv_b200_ell* spmv_b200_ell_create(int rows, int cols, int width) {
+    try { return reinterpret_cast<spmv_b200_ell*>(ell_create(rows, cols, width)); } catch (...) { return nullptr; }
+}
+void spmv_b200_ell_destroy(spmv_b200_ell* m) { ell_destroy(cpp(m)); }
+int spmv_b200_ell_from_dense(spmv_b200_ell* m, const float* dense, int rows, int cols) {
+    return guarded([&] { return ell_from_dense(cpp(m), dense, rows, cols); });
+}
+int spmv_b200_ell_from_csr(spmv_b200_ell* m, const spmv_b200_csr* csr) { return guarded([&] { return ell_from_csr(cpp(m), cpp(csr)); }); }
+int spmv_b200_ell_to_dense(const spmv_b200_ell* m, float* dense) { return guarded([&] { return ell_to_dense(cpp(m), dense); }); }
+float spmv_b200_ell_get_element(const spmv_b200_ell* m, int row, int col) { return ell_get_element(cpp(m), row, col); }
+int spmv_b200_ell_to_gpu(spmv_b200_ell* m) { return guarded([&] { return ell_to_gpu(cpp(m)); }); }
+int spmv_b200_ell_from_gpu(spmv_b200_ell* m) { return guarded([&] { return ell_from_gpu(cpp(m)); }); }
+void spmv_b200_ell_free_gpu(spmv_b200_ell* m) { ell_free_gpu(cpp(m)); }
+int spmv_b200_ell_serialize(const spmv_b200_ell* m, const char* f) { return guarded([&] { return ell_serialize(cpp(m), f); }); }
+int spmv_b200_ell_deserialize(spmv_b200_ell* m, const char* f) { return guarded([&] { return ell_deserialize(cpp(m), f); }); }
+int spmv_b200_ell_index(int row, int k, int num_rows) { return ell_index(row, k, num_rows); }
+
+// ---- C. SpMV ----------------------------------------------------------------------
+void spmv_b200_spmv_cpu_csr(const spmv_b200_csr* A, const float* x, float* y) { spmv_cpu_csr(cpp(A), x, y); }
+void spmv_b200_spmv_cpu_ell(const spmv_b200_ell* A, const float* x, float* y) { spmv_cpu_ell(cpp(A), x, y); }
+
+int spmv_b200_spmv_csr(const spmv_b200_csr* A, const float* d_x, float* d_y, const spmv_b200_config* config,
+                       int vec_size, spmv_b200_result* out) {
+    return guarded([&] {
+        const SpMVResult r = spmv_csr(cpp(A), d_x, d_y, cpp(config), vec_size);
+        to_c(r, out);
+        return r.error_code;
+    });
+}
+int spmv_b200_spmv_ell(const spmv_b200_ell* A, const float* d_x, float* d_y, const spmv_b200_config* config,
+                       int vec_size, spmv_b200_result* out) {
+    return guarded([&] {
+        const SpMVResult r = spmv_ell(cpp(A), d_x, d_y, cpp(config), vec_size);
+        to_c(r, out);
+        return r.error_code;
+    });
+}
+int spmv_b200_auto_config(const spmv_b200_csr* A, spmv_b200_config* out) {
+    if (!A || !out) return kBadArg;  // the C++ call dereferences A unchecked, as the reference does
+    to_c(spmv_auto_config(cpp(A)), out);
+    return 0;
+}
+int spmv_b200_reference_policy(const spmv_b200_csr* A, spmv_b200_config* out) {
+    if (!A || !out) return kBadArg;
+    to_c(b200::reference_policy(cpp(A)), out);
+    return 0;
+}
+bool spmv_b200_validate_dimensions(int num_cols, int vec_size) { return spmv_validate_dimensions(num_cols, vec_size); }
+
+int spmv_b200_spmv_csr_async(const spmv_b200_csr* A, const float* d_x, float* d_y, const spmv_b200_config* config,
+                             void* stream) {
+    return guarded([&] { return b200::spmv_csr_async(cpp(A), d_x, d_y, cpp(config), static_cast<cudaStream_t>(stream)); });
+}
+int spmv_b200_spmv_ell_async(const spmv_b200_ell* A, const float* d_x, float* d_y, void* stream) {
+    return guarded([&] { return b200::spmv_ell_async(cpp(A), d_x, d_y, static_cast<cudaStream_t>(stream)); });
+}
+
+// ---- D. bandwidth / PageRank / benchmark ------------------------------------------------
+int spmv_b200_bandwidth_csr(const spmv_b200_csr* A, float ms, spmv_b200_bandwidth* out) {
+    if (!out) return kBadArg;
+    to_c(compute_bandwidth_csr(cpp(A), ms), out);
+    return 0;
+}
+int spmv_b200_bandwidth_ell(const spmv_b200_ell* A, float ms, spmv_b200_bandwidth* out) {
+    if (!out) return kBadArg;
+    to_c(compute_bandwidth_ell(cpp(A), ms), out);
+    return 0;
+}
+float spmv_b200_peak_bandwidth(void) { return get_gpu_peak_bandwidth(); }
+
+int spmv_b200_pagerank(const spmv_b200_csr* adj, const spmv_b200_pagerank_config* config,
+                       spmv_b200_pagerank_result* out) {
+    if (!out) return kBadArg;
+    return guarded([&] {
+        const PageRankResult r = pagerank(cpp(adj), cpp(config));
+        out->ranks = r.ranks;
+        out->iterations = r.iterations;
+        out->final_residual = r.final_residual;
+        out->converged = r.converged;
+        return 0;
+    });
+}
+void spmv_b200_pagerank_free(spmv_b200_pagerank_result* r) { pagerank_free(reinterpret_cast<PageRankResult*>(r)); }
+int spmv_b200_pagerank_top_k(const spmv_b200_pagerank_result* r, int num_nodes, int k, spmv_b200_topk_node* top_k) {
+    if (!r || !r->ranks || !top_k || k <= 0) return kBadArg;
+    return guarded([&] {
+        pagerank_top_k(reinterpret_cast<const PageRankResult*>(r), num_nodes, k, reinterpret_cast<TopKNode*>(top_k));
+        return 0;
+    });
+}
+
+int spmv_b200_benchmark_csr(const spmv_b200_csr* A, const float* x, const spmv_b200_config* config,
+                            const spmv_b200_bench_config* bc, spmv_b200_bench_result* out) {
+    if (!A || !x || !out) return kBadArg;
+    return guarded([&] {
+        to_c(benchmark_csr(cpp(A), x, cpp(config), cpp(bc)), out);
+        return 0;
+    });
+}
+int spmv_b200_benchmark_ell(const spmv_b200_ell* A, const float* x, const spmv_b200_bench_config* bc,
+                            spmv_b200_bench_result* out) {
+    if (!A || !x || !out) return kBadArg;
+    return guarded([&] {
+        to_c(benchmark_ell(cpp(A), x, cpp(bc)), out);
+        return 0;
+    });
+}
+int spmv_b200_compare_gpu_cpu_csr(const spmv_b200_csr* A, const float* x, const spmv_b200_config* config,
+                                  const spmv_b200_bench_config* bc, spmv_b200_bench_result* gpu_out,
+                                  spmv_b200_bench_result* cpu_out, float* speedup) {
+    if (!A || !x) return kBadArg;
+    return guarded([&] {
+        const ComparisonResult c = compare_gpu_cpu_csr(cpp(A), x, cpp(config), cpp(bc));
+        to_c(c.gpu_result, gpu_out);
+        to_c(c.cpu_result, cpu_out);
+        if (speedup) *speedup = c.speedup;
+        return 0;
+    });
+}
+int spmv_b200_benchmark_to_json(const spmv_b200_bench_result* r, char* buf, int cap) {
+    if (!r || !buf || cap <= 0) return -1;
+    try {
+        const std::string s = benchmark_to_json(from_c(r));
+        if (static_cast<int>(s.size()) + 1 > cap) return -1;
+        std::memcpy(buf, s.c_str(), s.size() + 1);
+        return static_cast<int>(s.size());
+    } catch (...) {
+        return -1;
+    }
+}
+int spmv_b200_benchmark_from_json(const char* json, spmv_b200_bench_result* out) {
+    if (!json || !out) return kBadArg;
+    return guarded([&] {
+        to_c(benchmark_from_json(json), out);
+        return 0;
+    });
+}
+
+// ---- E. extensions ----------------------------------------------------------------------
+
+int spmv_b200_ell_from_csr_device(spmv_b200_ell* ell_c, const spmv_b200_csr* csr_c) {
+    ELLMatrix* ell = cpp(ell_c);
+    const CSRMatrix* csr = cpp(csr_c);
+    if (!ell || !csr) return kBadArg;
+    if (!csr->d_row_ptrs || (csr->nnz > 0 && (!csr->d_col_indices || !csr->d_values))) return SPMV_B200_INVALID_FORMAT;
+    return guarded([&] {
+        ell_free_gpu(ell);
+        const b200::CsrView A = b200::view_of(csr);
+        int width = 0;
+        if (A.rows > 0) {
+            int* d_w = nullptr;
+            CUDA_CHECK(cudaMalloc(&d_w, sizeof(int)));
+            cudaMemset(d_w, 0, sizeof(int));
+            b200::launch_max_row_len(A, d_w, nullptr);
+            cudaError_t e = cudaMemcpy(&width, d_w, sizeof(int), cudaMemcpyDeviceToHost);
+            cudaFree(d_w);
+            if (e != cudaSuccess) return static_cast<int>(SPMV_B200_CUDA_MEMCPY);
+        }
+        ell->num_rows = csr->num_rows;
+        ell->num_cols = csr->num_cols;
+        ell->max_nnz_per_row = width;
+        const size_t slots = static_cast<size_t>(A.rows > 0 ? A.rows : 0) * width;
+        if (slots) {
+            CUDA_CHECK(cudaMalloc(&ell->d_values, slots * sizeof(float)));
+            CUDA_CHECK(cudaMalloc(&ell->d_col_indices, slots * sizeof(int)));
+            if (b200::launch_ell_from_csr(A, width, ell->d_values, ell->d_col_indices, nullptr) != cudaSuccess)
+                return static_cast<int>(SPMV_B200_KERNEL_LAUNCH);
+            CUDA_CHECK(cudaDeviceSynchronize());
+        }
+        ell->owns_device_memory = true;
+        return 0;
+    });
+}
+
+int spmv_b200_merge_path_search(int diagonal, const int* row_ptrs, int num_rows, int nnz, int* out_row, int* out_nz) {
+    if (!row_ptrs || !out_row || !out_nz || diagonal < 0 || static_cast<long long>(diagonal) > static_cast<long long>(num_rows) + nnz)
+        return kBadArg;
+    int lo = diagonal - nnz > 0 ? diagonal - nnz : 0;
+    int hi = diagonal < num_rows ? diagonal : num_rows;
+    while (lo < hi) {  // same predicate as diagonal_search_global in csr_merge_kernels.cu
+        const int mid = lo + ((hi - lo) >> 1);
+        if (row_ptrs[mid + 1] <= diagonal - mid - 1) lo = mid + 1;
+        else hi = mid;
+    }
+    *out_row = lo;
+    *out_nz = diagonal - lo;
+    return 0;
+}
+
+// nnz-balanced contiguous row split: bounds[p] = first row whose start offset
+// is >= p * nnz / parts.
+int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, int parts, int* bounds) {
+    if (!row_ptrs || !bounds || num_rows < 0 || parts <= 0) return kBadArg;
+    const long long nnz = row_ptrs[num_rows];
+    bounds[0] = 0;
+    for (int p = 1; p < parts; ++p) {
+        const long long target = nnz * p / parts;
+        int lo = 0, hi = num_rows;
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if (row_ptrs[mid] < target) lo = mid + 1;
+            else hi = mid;
+        }
+        bounds[p] = lo < bounds[p - 1] ? bounds[p - 1] : lo;
+    }
+    bounds[parts] = num_rows;
+    return 0;
+}
+
+int spmv_b200_pr_plan_create(const spmv_b200_csr* shard, int row_offset, int n_global, void* stream,
+                             spmv_b200_pr_plan** out) {
+    return guarded([&] {
+        return b200::pr_plan_create(cpp(shard), row_offset, n_global, static_cast<cudaStream_t>(stream),
+                                    reinterpret_cast<b200::PrPlan**>(out));
+    });
+}
+void spmv_b200_pr_plan_destroy(spmv_b200_pr_plan* plan) { b200::pr_plan_destroy(reinterpret_cast<b200::PrPlan*>(plan)); }
+
+int spmv_b200_pr_colsum(const spmv_b200_pr_plan* plan, float* d_colsum, void* stream) {
+    if (!plan || !d_colsum) return kBadArg;
+    const cudaError_t e = b200::launch_colsum(b200::pr_plan_view(reinterpret_cast<const b200::PrPlan*>(plan)), d_colsum,
+                                              static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : SPMV_B200_KERNEL_LAUNCH;
+}
+int spmv_b200_pr_dangling_bits(const float* d_colsum, int n, uint32_t* d_bits, void* stream) {
+    if (!d_colsum || !d_bits || n < 0) return kBadArg;
+    return b200::launch_dangling_bits(d_colsum, n, n, d_bits, static_cast<cudaStream_t>(stream)) == cudaSuccess
+               ? 0 : SPMV_B200_KERNEL_LAUNCH;
+}
+int spmv_b200_pr_init(int n, const uint32_t* d_bits, float* d_r, float* d_dsum, void* stream) {
+    if (!d_bits || !d_r || !d_dsum || n < 0) return kBadArg;
+    return guarded([&] {
+        double* tmp = nullptr;
+        CUDA_CHECK(cudaMalloc(&tmp, sizeof(double) * (148 * 16 + 8)));
+        const cudaError_t e = b200::launch_pr_init(n, d_bits, d_r, d_dsum, tmp, static_cast<cudaStream_t>(stream));
+        cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+        cudaFree(tmp);
+        return e == cudaSuccess ? 0 : static_cast<int>(SPMV_B200_KERNEL_LAUNCH);
+    });
+}
+int spmv_b200_pr_step(spmv_b200_pr_plan* plan, const float* d_r_old, float* d_r_new, float damping,
+                      const float* d_dsum, const uint32_t* d_bits, double* d_partial, void* stream) {
+    return guarded([&] {
+        return b200::pr_step(reinterpret_cast<b200::PrPlan*>(plan), d_r_old, d_r_new, damping, d_dsum, d_bits, d_partial,
+                             static_cast<cudaStream_t>(stream));
+    });
+}
+int spmv_b200_pr_normalize(const float* d_r, int n, float* d_out, void* stream) {
+    if (!d_r || !d_out || n < 0) return kBadArg;
+    return guarded([&] {
+        double* tmp = nullptr;
+        CUDA_CHECK(cudaMalloc(&tmp, sizeof(double) * (148 * 16 + 8)));
+        const cudaError_t e = b200::launch_normalize(d_r, n, d_out, tmp, static_cast<cudaStream_t>(stream));
+        cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+        cudaFree(tmp);
+        return e == cudaSuccess ? 0 : static_cast<int>(SPMV_B200_KERNEL_LAUNCH);
+    });
+}
+
+int spmv_b200_pagerank_device(const spmv_b200_csr* adj, const spmv_b200_pagerank_config* config, float* d_ranks,
+                              int* iterations, float* final_residual, bool* converged, double* l1_residual) {
+    return guarded([&] {
+        return b200::pagerank_device(cpp(adj), cpp(config), d_ranks, iterations, final_residual, converged, l1_residual);
+    });
+}
+
+}  // extern "C"

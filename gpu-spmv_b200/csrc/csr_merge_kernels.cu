@@ -1,0 +1,408 @@
+// csr_merge_kernels.cu -- two-level merge-path CSR SpMV for sm_100a, and the
+// fused PageRank iteration built on it.
+//
+// Replaces merge_path_search + spmv_csr_merge_path_kernel + the pre-launch
+// cudaMemset (reference src/spmv_kernels.cu:48-72, :75-130, :267).  The
+// reference gives every THREAD its own diagonal (two global binary searches
+// per thread), walks its non-zeros uncoalesced and commits rows with float
+// atomics; its search is also off by one, so its results are
+// wrong.  This implementation uses the canonical Merrill-Garland formulation:
+//
+//   level 1  merge_partition_kernel: one search per TILE of kMergeTile merge
+//            items (rows + nnz are the two merged lists) -> coords[].
+//   level 2  merge_tile_kernel: a CTA takes one tile.  It stages the tile's
+//            row-end offsets in shared memory, streams the tile's contiguous
+//            non-zero range with coalesced 128-bit loads of values and
+//            col_indices, gathers x and parks the products in shared memory.
+//            Every thread then locates its own diagonal by a binary search IN
+//            SHARED MEMORY and consumes kMergeItemsPerThread items serially.
+//            Rows that start inside a thread are finished by that thread; the
+//            row open at a thread boundary is resolved by a warp-shuffle
+//            segmented scan over (emitted?, carry) pairs plus an 8-entry
+//            cross-warp fold.  The row left open at the tile end goes to
+//            carry_row/carry_val.
+//   level 3  merge_fixup_kernel: for every run of tiles that left the same row
+//            open, one thread adds the run's carries (in tile order) to that
+//            row.  No float atomics and no pre-zeroing of y: every row is
+//            written exactly once by level 2 and touched by at most one
+//            thread of level 3, so results are deterministic.
+//
+// The row epilogue is a template parameter.  PlainRow writes y.  PageRankRow
+// applies r_new = (d*y + d*dangling/n) + (1-d)/n in the reference's operation
+// order (src/pagerank.cu:111-114), and accumulates sum (r_new-r_old)^2,
+// sum |r_new-r_old| and the next iteration's dangling mass in f64 -- SpMV,
+// damping/teleport, dangling mass and residual in ONE pass over the matrix.
+//
+// Roofline: HBM.  Algorithmic bytes per launch = 8*nnz + 4*(rows+1) + 4*cols +
+// 4*rows (reference src/bandwidth.cpp:34-42); merge-path timing includes
+// partition + tile + fix-up, as the reference's includes its memset.
+#include "device_utils.cuh"
+#include "internal.hpp"
+
+#include <climits>
+
+namespace spmv {
+namespace b200 {
+
+// ------------------------------------------------------------ plan layout ----
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int fixup_blocks_for(int num_tiles) { return (num_tiles + 255) / 256; }
+
+size_t merge_plan_bytes(int rows, int nnz, bool with_partials) {
+    const size_t tiles = static_cast<size_t>(merge_num_tiles(rows, nnz));
+    size_t b = align_up((tiles + 1) * sizeof(int2), 256);
+    b += align_up(tiles * sizeof(int), 256);
+    b += align_up(tiles * sizeof(float), 256);
+    if (with_partials) b += align_up((tiles + fixup_blocks_for(static_cast<int>(tiles))) * 3 * sizeof(double), 256);
+    return b + 256;
+}
+
+MergePlan merge_plan_carve(void* block, int rows, int nnz, bool with_partials) {
+    MergePlan p;
+    p.num_tiles = merge_num_tiles(rows, nnz);
+    p.fixup_blocks = fixup_blocks_for(p.num_tiles);
+    const size_t tiles = static_cast<size_t>(p.num_tiles);
+    unsigned char* at = static_cast<unsigned char*>(block);
+    p.coords = reinterpret_cast<int2*>(at);
+    at += align_up((tiles + 1) * sizeof(int2), 256);
+    p.carry_row = reinterpret_cast<int*>(at);
+    at += align_up(tiles * sizeof(int), 256);
+    p.carry_val = reinterpret_cast<float*>(at);
+    at += align_up(tiles * sizeof(float), 256);
+    p.partials = with_partials ? reinterpret_cast<double*>(at) : nullptr;
+    return p;
+}
+
+namespace {
+
+constexpr int kT = kMergeThreads;
+constexpr int kIPT = kMergeItemsPerThread;
+constexpr int kTile = kMergeTile;
+
+// ---------------------------------------------------------------- level 1 ----
+// Canonical diagonal search: list A = row END offsets row_ptrs[1..rows], list
+// B = non-zero indices 0..nnz-1; A wins ties (a row ends before the non-zero
+// with the same index is consumed).
+__device__ __forceinline__ int2 diagonal_search_global(int diagonal, const int* __restrict__ row_ptrs,
+                                                       int rows, int nnz) {
+    int lo = max(diagonal - nnz, 0);
+    int hi = min(diagonal, rows);
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (__ldg(row_ptrs + mid + 1) <= diagonal - mid - 1) lo = mid + 1;
+        else hi = mid;
+    }
+    return make_int2(lo, diagonal - lo);
+}
+
+__global__ void merge_partition_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
+                                       int num_tiles, int2* __restrict__ coords) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > num_tiles) return;
+    const long long total = static_cast<long long>(rows) + nnz;
+    const long long d = static_cast<long long>(t) * kTile;
+    coords[t] = diagonal_search_global(static_cast<int>(d < total ? d : total), row_ptrs, rows, nnz);
+}
+
+// -------------------------------------------------------------- epilogues ----
+
+struct NoSums {
+    __device__ __forceinline__ void clear() {}
+};
+struct RankSums {
+    double l2, l1, dangling;
+    __device__ __forceinline__ void clear() { l2 = 0.0; l1 = 0.0; dangling = 0.0; }
+};
+
+// y[row] = sum
+struct PlainRow {
+    using Sums = NoSums;
+    static constexpr bool kReduces = false;
+    float* y;
+    __device__ __forceinline__ void prepare() {}
+    __device__ __forceinline__ void finish(int row, float sum, Sums&) const { y[row] = sum; }
+    __device__ __forceinline__ void park(int row, float partial) const { y[row] = partial; }
+    __device__ __forceinline__ float parked(int row) const { return y[row]; }
+};
+
+// fused PageRank update of one finished row
+struct PageRankRow {
+    using Sums = RankSums;
+    static constexpr bool kReduces = true;
+    PageRankStepArgs a;
+    float dangling_term;  // d * dsum / n, set by prepare()
+    __device__ __forceinline__ void prepare() {
+        // reference src/pagerank.cu:111: damping * dangling_sum / n, evaluated left to right in fp32
+        dangling_term = __fdiv_rn(__fmul_rn(a.damping, *a.d_dsum), static_cast<float>(a.n_global));
+    }
+    __device__ __forceinline__ void finish(int row, float sum, Sums& s) const {
+        const int g = a.row_offset + row;
+        // reference src/pagerank.cu:113: (damping * y + dangling_contrib) + teleport
+        const float v = __fadd_rn(__fadd_rn(__fmul_rn(a.damping, sum), dangling_term), a.teleport);
+        a.r_new[g] = v;
+        const double diff = static_cast<double>(v) - static_cast<double>(a.r_old[g]);
+        s.l2 += diff * diff;
+        s.l1 += fabs(diff);
+        if ((a.bits[g >> 5] >> (g & 31)) & 1u) s.dangling += static_cast<double>(v);
+    }
+    __device__ __forceinline__ void park(int row, float partial) const { a.r_new[a.row_offset + row] = partial; }
+    __device__ __forceinline__ float parked(int row) const { return a.r_new[a.row_offset + row]; }
+};
+
+// block-wide sum of RankSums into partials[slot*3 .. +3] (fixed order)
+__device__ __forceinline__ void block_store_sums(const RankSums& s, double* __restrict__ partials, int slot,
+                                                 double (*scratch)[3]) {
+    double a = dev::warp_sum(s.l2), b = dev::warp_sum(s.l1), c = dev::warp_sum(s.dangling);
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { scratch[warp][0] = a; scratch[warp][1] = b; scratch[warp][2] = c; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < kT / 32; ++w) t += scratch[w][threadIdx.x];
+        partials[static_cast<size_t>(slot) * 3 + threadIdx.x] = t;
+    }
+}
+__device__ __forceinline__ void block_store_sums(const NoSums&, double*, int, double (*)[3]) {}
+
+// ---------------------------------------------------------------- level 2 ----
+
+template <class Row>
+__global__ void __launch_bounds__(kT)
+merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
+                  const int* __restrict__ col_indices, const float* __restrict__ values,
+                  const float* __restrict__ x, const int2* __restrict__ coords,
+                  int* __restrict__ carry_row, float* __restrict__ carry_val, Row row_op,
+                  double* __restrict__ partials) {
+    __shared__ int s_end[kTile + 1];            // global END offset of tile-local row i
+    __shared__ __align__(16) float s_prod[kTile + 4];
+    __shared__ float s_warp_val[kT / 32];
+    __shared__ int s_warp_flag[kT / 32];
+    __shared__ double s_sums[kT / 32][3];
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int2 c0 = coords[tile];
+    const int2 c1 = coords[tile + 1];
+    const int row_s = c0.x, nz_s = c0.y;
+    const int tile_rows = c1.x - c0.x;  // row-end items in this tile
+    const int tile_nz = c1.y - c0.y;    // non-zero items in this tile
+    const int tile_items = tile_rows + tile_nz;
+    const int nz_e = c1.y;
+
+    row_op.prepare();
+
+    // ---- stage row ends (tile_rows + 1 entries; the last one bounds the open row)
+    for (int i = tid; i <= tile_rows; i += kT)
+        s_end[i] = (row_s + i < rows) ? dev::ld_stream_i(row_ptrs + row_s + 1 + i) : INT_MAX;
+
+    // ---- stage products of non-zeros [nz_s, nz_e) at slot (j - base) ----------
+    const int base = nz_s & ~3;
+    for (int j = base + 4 * tid; j < nz_e; j += 4 * kT) {
+        float p0, p1, p2, p3;
+        if (j >= nz_s && j + 4 <= nz_e) {
+            const float4 v = dev::ld_stream_f4(values + j);
+            const int4 c = dev::ld_stream_i4(col_indices + j);
+            p0 = v.x * dev::ld_x(x + c.x);
+            p1 = v.y * dev::ld_x(x + c.y);
+            p2 = v.z * dev::ld_x(x + c.z);
+            p3 = v.w * dev::ld_x(x + c.w);
+        } else {
+            p0 = (j + 0 >= nz_s && j + 0 < nz_e) ? values[j + 0] * dev::ld_x(x + col_indices[j + 0]) : 0.0f;
+            p1 = (j + 1 >= nz_s && j + 1 < nz_e) ? values[j + 1] * dev::ld_x(x + col_indices[j + 1]) : 0.0f;
+            p2 = (j + 2 >= nz_s && j + 2 < nz_e) ? values[j + 2] * dev::ld_x(x + col_indices[j + 2]) : 0.0f;
+            p3 = (j + 3 >= nz_s && j + 3 < nz_e) ? values[j + 3] * dev::ld_x(x + col_indices[j + 3]) : 0.0f;
+        }
+        *reinterpret_cast<float4*>(s_prod + (j - base)) = make_float4(p0, p1, p2, p3);
+    }
+    // does the tile's first row own non-zeros in earlier tiles?
+    const bool first_row_split = (row_s < rows) && (nz_s > __ldg(row_ptrs + row_s));
+    __syncthreads();
+
+    // ---- per-thread diagonal inside the tile (search in shared memory) ---------
+    const int diag = min(tid * kIPT, tile_items);
+    int lo = max(diag - tile_nz, 0);
+    int hi = min(diag, tile_rows);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_end[mid] <= nz_s + (diag - mid - 1)) lo = mid + 1;
+        else hi = mid;
+    }
+    int r = lo;                  // tile-local row
+    int z = nz_s + (diag - lo);  // global non-zero index
+    const int my_items = min(kIPT, tile_items - diag);
+
+    typename Row::Sums sums;
+    sums.clear();
+
+    float running = 0.0f;
+    bool emitted = false;
+    float first_sum = 0.0f;
+    int first_row = 0;
+    int row_end = s_end[r];
+#pragma unroll
+    for (int it = 0; it < kIPT; ++it) {
+        if (it < my_items) {
+            if (z < row_end) {
+                running += s_prod[z - base];
+                ++z;
+            } else {
+                if (!emitted) {  // may still need the carry of earlier threads
+                    emitted = true;
+                    first_sum = running;
+                    first_row = r;
+                } else {
+                    row_op.finish(row_s + r, running, sums);
+                }
+                running = 0.0f;
+                ++r;
+                row_end = s_end[r];
+            }
+        }
+    }
+
+    // ---- segmented scan of (emitted, running) over the CTA ----------------------
+    // combine(earlier, later) = (fe | fl, fl ? vl : ve + vl)
+    const int lane = tid & 31, warp = tid >> 5;
+    float v = running;
+    int f = emitted ? 1 : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float pv = __shfl_up_sync(0xffffffffu, v, d);
+        const int pf = __shfl_up_sync(0xffffffffu, f, d);
+        if (lane >= d) {
+            if (!f) v = pv + v;
+            f |= pf;
+        }
+    }
+    // exclusive prefix inside the warp
+    float ex_v = __shfl_up_sync(0xffffffffu, v, 1);
+    int ex_f = __shfl_up_sync(0xffffffffu, f, 1);
+    if (lane == 0) { ex_v = 0.0f; ex_f = 0; }
+    if (lane == 31) { s_warp_val[warp] = v; s_warp_flag[warp] = f; }
+    __syncthreads();
+    // fold the aggregates of the preceding warps
+    float pre_v = 0.0f;
+    int pre_f = 0;
+    for (int w = 0; w < warp; ++w) {
+        const float wv = s_warp_val[w];
+        const int wf = s_warp_flag[w];
+        pre_v = wf ? wv : pre_v + wv;
+        pre_f |= wf;
+    }
+    const float carry_in = ex_f ? ex_v : pre_v + ex_v;
+
+    if (emitted) {
+        const float total = carry_in + first_sum;
+        if (first_row == 0 && first_row_split) row_op.park(row_s, total);  // level 3 finishes it
+        else row_op.finish(row_s + first_row, total, sums);
+    }
+
+    // ---- tile carry-out: the row still open at the tile end ------------------------
+    if (tid == kT - 1) {
+        const float open_sum = f ? v : pre_v + v;  // inclusive scan value of the last thread
+        const int row_e = c1.x;
+        const int open_start = tile_rows > 0 ? s_end[tile_rows - 1] : (row_s < rows ? __ldg(row_ptrs + row_s) : nz_e);
+        const bool has_open = (row_e < rows) && (nz_e > max(open_start, nz_s));
+        carry_row[tile] = has_open ? row_e : -1;
+        carry_val[tile] = has_open ? open_sum : 0.0f;
+    }
+
+    if (Row::kReduces) block_store_sums(sums, partials, tile, s_sums);
+}
+
+// ---------------------------------------------------------------- level 3 ----
+
+template <class Row>
+__global__ void __launch_bounds__(256)
+merge_fixup_kernel(int num_tiles, const int* __restrict__ carry_row, const float* __restrict__ carry_val,
+                   Row row_op, double* __restrict__ partials) {
+    __shared__ double s_sums[256 / 32][3];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    typename Row::Sums sums;
+    sums.clear();
+    row_op.prepare();
+    if (t < num_tiles) {
+        const int row = carry_row[t];
+        if (row >= 0 && (t == 0 || carry_row[t - 1] != row)) {  // leader of a run of tiles
+            float total = carry_val[t];
+            for (int u = t + 1; u < num_tiles && carry_row[u] == row; ++u) total += carry_val[u];
+            // the tile in which the row ends parked its own share
+            row_op.finish(row, row_op.parked(row) + total, sums);
+        }
+    }
+    if (Row::kReduces) block_store_sums(sums, partials, num_tiles + blockIdx.x, s_sums);
+}
+
+// final deterministic reduction of the per-CTA partial sums -> out[3]
+__global__ void __launch_bounds__(1024)
+reduce_partials_kernel(const double* __restrict__ partials, int count, double* __restrict__ out) {
+    __shared__ double s[32][3];
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < count; i += 1024) {
+        a += partials[static_cast<size_t>(i) * 3 + 0];
+        b += partials[static_cast<size_t>(i) * 3 + 1];
+        c += partials[static_cast<size_t>(i) * 3 + 2];
+    }
+    a = dev::warp_sum(a); b = dev::warp_sum(b); c = dev::warp_sum(c);
+    if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5][0] = a; s[threadIdx.x >> 5][1] = b; s[threadIdx.x >> 5][2] = c; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += s[w][threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+}
+
+__global__ void zero_rows_kernel(int rows, float* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) y[i] = 0.0f;
+}
+
+template <class Row>
+cudaError_t run_tiles(const CsrView& A, const float* x, const MergePlan& plan, const Row& row_op,
+                      cudaStream_t stream) {
+    if (plan.num_tiles <= 0) return cudaSuccess;
+    merge_tile_kernel<Row><<<plan.num_tiles, kT, 0, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values, x,
+                                                              plan.coords, plan.carry_row, plan.carry_val, row_op,
+                                                              plan.partials);
+    merge_fixup_kernel<Row><<<plan.fixup_blocks, 256, 0, stream>>>(plan.num_tiles, plan.carry_row, plan.carry_val,
+                                                                   row_op, plan.partials);
+    count_launches(2);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_merge_partition(const CsrView& A, const MergePlan& plan, cudaStream_t stream) {
+    if (plan.num_tiles <= 0) return cudaSuccess;
+    const int n = plan.num_tiles + 1;
+    merge_partition_kernel<<<(n + 255) / 256, 256, 0, stream>>>(A.rows, A.nnz, A.row_ptrs, plan.num_tiles, plan.coords);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_spmv(const CsrView& A, const float* x, float* y, const MergePlan& plan,
+                              cudaStream_t stream) {
+    if (A.rows <= 0) return cudaSuccess;
+    PlainRow op{y};
+    return run_tiles(A, x, plan, op, stream);
+}
+
+cudaError_t launch_merge_pagerank(const CsrView& A, const MergePlan& plan, const PageRankStepArgs& args,
+                                  cudaStream_t stream) {
+    if (A.rows <= 0) {
+        cudaError_t e = cudaMemsetAsync(args.out, 0, 3 * sizeof(double), stream);
+        return e;
+    }
+    PageRankRow op{args, 0.0f};
+    cudaError_t e = run_tiles(A, args.r_old, plan, op, stream);
+    if (e != cudaSuccess) return e;
+    reduce_partials_kernel<<<1, 1024, 0, stream>>>(plan.partials, plan.num_tiles + plan.fixup_blocks, args.out);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+}  // namespace b200
+}  // namespace spmv

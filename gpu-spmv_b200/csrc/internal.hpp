@@ -1,0 +1,151 @@
+// internal.hpp -- declarations shared between the translation units of
+// libspmv_b200.so.  Not installed; the public surfaces are
+// include/spmv_b200/api.hpp (C++) and include/spmv_b200.h (C ABI).
+#pragma once
+
+#include "spmv_b200/api.hpp"
+
+#include <cstddef>
+#include <cstdint>
+
+namespace spmv {
+namespace b200 {
+
+// ---- selector -----------------------------------------------------------------
+// A SCALAR_CSR decision is overridden to MERGE_PATH when a row is longer than
+// this (one CTA of the row-owner kernel would otherwise walk it alone).
+constexpr int kOutlierRowNnz = 65536;
+
+SpMVConfig::KernelType reference_kernel_choice(const CSRStats& s);
+SpMVConfig reference_policy(const CSRMatrix* A);
+
+size_t csr_compulsory_bytes(const CSRMatrix* A);
+size_t ell_compulsory_bytes(const ELLMatrix* A);
+
+// ---- launch accounting ----------------------------------------------------------
+void count_launches(int n);
+unsigned long long launch_count();
+
+// ---- device views ----------------------------------------------------------------
+struct CsrView {
+    int rows;
+    int cols;
+    int nnz;
+    const int* row_ptrs;     // device [rows + 1]
+    const int* col_indices;  // device [nnz]
+    const float* values;     // device [nnz]
+};
+
+inline CsrView view_of(const CSRMatrix* A) {
+    return CsrView{A->num_rows, A->num_cols, A->nnz, A->d_row_ptrs, A->d_col_indices, A->d_values};
+}
+
+// Grow-only device scratch (per owner; not thread-safe).
+class Scratch {
+public:
+    Scratch() = default;
+    ~Scratch();
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    // returns nullptr on allocation failure
+    void* reserve(size_t bytes);
+    void release();
+private:
+    void* ptr_ = nullptr;
+    size_t cap_ = 0;
+};
+
+// ---- merge-path geometry (shared by host planning and the kernels) ---------------
+constexpr int kMergeThreads = 256;
+constexpr int kMergeItemsPerThread = 8;
+constexpr int kMergeTile = kMergeThreads * kMergeItemsPerThread;  // merge items per CTA
+
+struct MergePlan {
+    int num_tiles = 0;
+    int2* coords = nullptr;      // [num_tiles + 1] (row, nz) at every tile diagonal
+    int* carry_row = nullptr;    // [num_tiles] row left open at the tile end, or -1
+    float* carry_val = nullptr;  // [num_tiles] its partial sum inside the tile
+    double* partials = nullptr;  // [(num_tiles + fixup_blocks) * 3] fused-PageRank sums
+    int fixup_blocks = 0;
+};
+
+inline int merge_num_tiles(int rows, int nnz) {
+    const long long items = static_cast<long long>(rows) + nnz;
+    return static_cast<int>((items + kMergeTile - 1) / kMergeTile);
+}
+size_t merge_plan_bytes(int rows, int nnz, bool with_partials);
+// carve a MergePlan out of a scratch block of merge_plan_bytes() bytes
+MergePlan merge_plan_carve(void* block, int rows, int nnz, bool with_partials);
+
+// ---- fused PageRank epilogue parameters ---------------------------------------------
+struct PageRankStepArgs {
+    const float* r_old;     // full vector [n_global]
+    float* r_new;           // full vector [n_global]
+    int row_offset;         // first global row of this shard
+    int n_global;
+    float damping;
+    float teleport;         // (1 - d) / n, computed on the host in fp32
+    const float* d_dsum;    // device scalar: dangling mass of r_old
+    const uint32_t* bits;   // dangling bitmask over global node ids
+    double* out;            // device [3]: sum d^2, sum |d|, next dangling mass
+};
+
+// ---- kernel launchers (stream-ordered; return the launch status) --------------------
+cudaError_t launch_ell(int rows, int width, const int* col_indices, const float* values,
+                       const float* x, float* y, unsigned long long* nnz_counter,
+                       cudaStream_t stream);
+
+// Row-owner kernel: lanes_per_row == 1 is the SCALAR_CSR path (sequential
+// per-row order, bit-identical to spmv_cpu_csr); 2..16 sub-warp VECTOR_CSR.
+cudaError_t launch_csr_stream(const CsrView& A, const float* x, float* y, int lanes_per_row,
+                              cudaStream_t stream);
+// One warp per row with 128-bit loads (VECTOR_CSR for long rows).
+cudaError_t launch_csr_warp_per_row(const CsrView& A, const float* x, float* y, cudaStream_t stream);
+// VECTOR_CSR front end: picks lanes per row from the average row length.
+cudaError_t launch_csr_vector(const CsrView& A, const float* x, float* y, cudaStream_t stream);
+int vector_lanes_for(int rows, int nnz);
+
+// Merge-path: partition (fills plan.coords) then tile + fix-up kernels.
+cudaError_t launch_merge_partition(const CsrView& A, const MergePlan& plan, cudaStream_t stream);
+cudaError_t launch_merge_spmv(const CsrView& A, const float* x, float* y, const MergePlan& plan,
+                              cudaStream_t stream);
+cudaError_t launch_merge_pagerank(const CsrView& A, const MergePlan& plan,
+                                  const PageRankStepArgs& args, cudaStream_t stream);
+
+// PageRank helpers
+cudaError_t launch_colsum(const CsrView& A, float* d_colsum, cudaStream_t stream);
+cudaError_t launch_dangling_bits(const float* d_colsum, int n, int valid_cols, uint32_t* d_bits,
+                                 cudaStream_t stream);
+cudaError_t launch_pr_init(int n, const uint32_t* d_bits, float* d_r, float* d_dsum,
+                           double* d_tmp, cudaStream_t stream);
+cudaError_t launch_next_dsum(const double* d_partial, float* d_dsum, cudaStream_t stream);
+cudaError_t launch_normalize(const float* d_r, int n, float* d_out, double* d_tmp,
+                             cudaStream_t stream);
+cudaError_t launch_ell_from_csr(const CsrView& A, int width, float* ell_values, int* ell_cols,
+                                cudaStream_t stream);
+cudaError_t launch_max_row_len(const CsrView& A, int* d_out, cudaStream_t stream);
+
+// ---- stream-ordered dispatch used by the blocking API, benchmark and PageRank --------
+// Chooses and launches the kernel(s) for `kernel_type` (any unknown value ->
+// SCALAR, as src/spmv_kernels.cu:287-288).  `scratch` backs merge-path plans.
+cudaError_t dispatch_csr(const CsrView& A, const float* x, float* y, int kernel_type,
+                         Scratch& scratch, cudaStream_t stream);
+
+// stream-ordered twins of spmv_csr / spmv_ell (no sync, no timing); return a SpMVError
+int spmv_csr_async(const CSRMatrix* A, const float* d_x, float* d_y, const SpMVConfig* config,
+                   cudaStream_t stream);
+int spmv_ell_async(const ELLMatrix* A, const float* d_x, float* d_y, cudaStream_t stream);
+
+// ---- PageRank plan over one row shard (pagerank.cu) -------------------------------------
+struct PrPlan;
+int pr_plan_create(const CSRMatrix* shard, int row_offset, int n_global, cudaStream_t stream, PrPlan** out);
+void pr_plan_destroy(PrPlan* plan);
+int pr_step(PrPlan* plan, const float* d_r_old, float* d_r_new, float damping, const float* d_dsum,
+            const uint32_t* d_bits, double* d_partial, cudaStream_t stream);
+const CsrView& pr_plan_view(const PrPlan* plan);
+double* pr_plan_tmp(PrPlan* plan);
+int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,
+                    float* final_residual, bool* converged, double* l1_residual);
+
+}  // namespace b200
+}  // namespace spmv

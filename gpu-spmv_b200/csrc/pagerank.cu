@@ -1,0 +1,231 @@
+// pagerank.cu -- PageRank on the fused merge-path iteration.
+//
+// Replaces pagerank() (reference src/pagerank.cu:50-153).  The reference runs
+// only the SpMV on the GPU and, EVERY iteration, copies the rank vector to the
+// host, applies damping/teleport/dangling mass there with single-threaded fp32
+// loops, copies it back and computes the L2 residual on the host.  Here the
+// whole iteration is one pass of merge_tile_kernel<PageRankRow> (+ its fix-up
+// and a 1-CTA reduction): the rank vectors never leave HBM and the only
+// per-iteration host traffic is the 24-byte {sum d^2, sum |d|, dangling mass}.
+//
+// Recurrence, initial vector, update expression order, stop rule (L2 norm of
+// the delta < tolerance, checked after every iteration), result fields and the
+// final normalisation follow the reference line by line; the three global
+// sums use f64 accumulators because the reference's sequential fp32 host sums
+// lose all accuracy at n = 2^26.
+//
+// The same building blocks work on a row shard of the matrix (row_offset,
+// n_global) so that one process per GPU can run a sharded PageRank with an
+// all-gather of the rank slices and an all-reduce of the three sums in between
+// (gpu-spmv_b200/dist.py).
+#include "internal.hpp"
+
+#include <cmath>
+#include <new>
+
+namespace spmv {
+namespace b200 {
+
+constexpr int kTmpDoubles = 148 * 16 + 8;
+
+// A plan over one row shard: merge-path coordinates are computed once (the
+// matrix is constant across iterations) and the work arrays are owned here.
+struct PrPlan {
+    CsrView A{};
+    int row_offset = 0;
+    int n_global = 0;
+    Scratch merge_block;
+    MergePlan merge;
+    Scratch tmp_block;   // kTmpDoubles doubles
+    double* tmp = nullptr;
+};
+
+int pr_plan_create(const CSRMatrix* shard, int row_offset, int n_global, cudaStream_t stream, PrPlan** out) {
+    if (!shard || !out || row_offset < 0 || n_global < 0) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
+    if (static_cast<long long>(row_offset) + shard->num_rows > n_global)
+        return static_cast<int>(SpMVError::INVALID_DIMENSION);
+    if (!shard->d_row_ptrs || (shard->nnz > 0 && (!shard->d_col_indices || !shard->d_values)))
+        return static_cast<int>(SpMVError::INVALID_FORMAT);
+    PrPlan* p = new (std::nothrow) PrPlan();
+    if (!p) return static_cast<int>(SpMVError::OUT_OF_MEMORY);
+    p->A = view_of(shard);
+    p->row_offset = row_offset;
+    p->n_global = n_global;
+    void* block = p->merge_block.reserve(merge_plan_bytes(p->A.rows, p->A.nnz, true));
+    p->tmp = static_cast<double*>(p->tmp_block.reserve(kTmpDoubles * sizeof(double)));
+    if (!block || !p->tmp) {
+        delete p;
+        return static_cast<int>(SpMVError::CUDA_MALLOC);
+    }
+    p->merge = merge_plan_carve(block, p->A.rows, p->A.nnz, true);
+    if (p->A.rows > 0 && launch_merge_partition(p->A, p->merge, stream) != cudaSuccess) {
+        cudaGetLastError();
+        delete p;
+        return static_cast<int>(SpMVError::KERNEL_LAUNCH);
+    }
+    *out = p;
+    return 0;
+}
+
+void pr_plan_destroy(PrPlan* p) { delete p; }
+
+int pr_step(PrPlan* p, const float* d_r_old, float* d_r_new, float damping, const float* d_dsum,
+            const uint32_t* d_bits, double* d_partial, cudaStream_t stream) {
+    if (!p || !d_r_old || !d_r_new || !d_dsum || !d_bits || !d_partial)
+        return static_cast<int>(SpMVError::INVALID_ARGUMENT);
+    PageRankStepArgs a;
+    a.r_old = d_r_old;
+    a.r_new = d_r_new;
+    a.row_offset = p->row_offset;
+    a.n_global = p->n_global;
+    a.damping = damping;
+    a.teleport = (1.0f - damping) / p->n_global;  // reference src/pagerank.cu:86
+    a.d_dsum = d_dsum;
+    a.bits = d_bits;
+    a.out = d_partial;
+    if (launch_merge_pagerank(p->A, p->merge, a, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return static_cast<int>(SpMVError::KERNEL_LAUNCH);
+    }
+    return 0;
+}
+
+const CsrView& pr_plan_view(const PrPlan* p) { return p->A; }
+double* pr_plan_tmp(PrPlan* p) { return p->tmp; }
+
+// The whole loop on one device; d_ranks receives the normalised ranks.
+int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,
+                    float* final_residual, bool* converged, double* l1_residual) {
+    if (!adj || !d_ranks) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
+    PageRankConfig defaults;
+    if (!config) config = &defaults;
+    const int n = adj->num_rows;
+    if (iterations) *iterations = 0;
+    if (final_residual) *final_residual = 0.0f;
+    if (converged) *converged = false;
+    if (l1_residual) *l1_residual = 0.0;
+    if (n <= 0) return 0;
+
+    cudaStream_t stream = nullptr;
+    PrPlan* plan = nullptr;
+    int rc = pr_plan_create(adj, 0, n, stream, &plan);
+    if (rc != 0) return rc;
+
+    const int cols = adj->num_cols;
+    const size_t colsum_n = static_cast<size_t>(cols > n ? cols : n);
+    const size_t words = (static_cast<size_t>(n) + 31) / 32;
+    float *d_a = nullptr, *d_b = nullptr, *d_colsum = nullptr, *d_dsum = nullptr;
+    uint32_t* d_bits = nullptr;
+    double* d_partial = nullptr;
+    double* h_partial = nullptr;
+    bool ok = cudaMalloc(&d_a, sizeof(float) * n) == cudaSuccess &&
+              cudaMalloc(&d_b, sizeof(float) * n) == cudaSuccess &&
+              cudaMalloc(&d_colsum, sizeof(float) * colsum_n) == cudaSuccess &&
+              cudaMalloc(&d_bits, sizeof(uint32_t) * words) == cudaSuccess &&
+              cudaMalloc(&d_dsum, sizeof(float)) == cudaSuccess &&
+              cudaMalloc(&d_partial, 3 * sizeof(double)) == cudaSuccess &&
+              cudaMallocHost(&h_partial, 3 * sizeof(double)) == cudaSuccess;
+    auto cleanup = [&]() {
+        cudaFree(d_a); cudaFree(d_b); cudaFree(d_colsum); cudaFree(d_bits); cudaFree(d_dsum); cudaFree(d_partial);
+        if (h_partial) cudaFreeHost(h_partial);
+        pr_plan_destroy(plan);
+    };
+    if (!ok) {
+        cudaGetLastError();
+        cleanup();
+        return static_cast<int>(SpMVError::CUDA_MALLOC);
+    }
+
+    // dangling nodes: columns whose stored values sum to 0 (reference :20-48, :87)
+    cudaMemsetAsync(d_colsum, 0, sizeof(float) * colsum_n, stream);
+    launch_colsum(plan->A, d_colsum, stream);
+    launch_dangling_bits(d_colsum, n, cols, d_bits, stream);
+    // r = 1/n and its dangling mass (reference :69-72, :94-99 for iteration 0)
+    launch_pr_init(n, d_bits, d_a, d_dsum, plan->tmp, stream);
+
+    float* r_old = d_a;
+    float* r_new = d_b;
+    bool from_new = false;
+    int iters = 0;
+    float residual = 0.0f;
+    double l1 = 0.0;
+    bool conv = false;
+    for (int it = 0; it < config->max_iterations; ++it) {
+        rc = pr_step(plan, r_old, r_new, config->damping_factor, d_dsum, d_bits, d_partial, stream);
+        if (rc != 0) break;  // the reference also leaves the loop on a failed SpMV (:105-107)
+        launch_next_dsum(d_partial, d_dsum, stream);
+        cudaMemcpyAsync(h_partial, d_partial, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
+        if (cudaStreamSynchronize(stream) != cudaSuccess) {
+            cudaGetLastError();
+            rc = static_cast<int>(SpMVError::KERNEL_LAUNCH);
+            break;
+        }
+        residual = std::sqrt(static_cast<float>(h_partial[0]));  // L2 norm of the delta (:118)
+        l1 = h_partial[1];
+        iters = it + 1;
+        if (residual < config->tolerance) {  // :123-127
+            conv = true;
+            from_new = true;
+            break;
+        }
+        float* t = r_old; r_old = r_new; r_new = t;  // :130-131
+    }
+    // final vector (:135-139) and normalisation (:142-150)
+    const float* fin = from_new ? r_new : r_old;
+    launch_normalize(fin, n, d_ranks, plan->tmp, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (rc == 0) rc = static_cast<int>(SpMVError::KERNEL_LAUNCH);
+    }
+    if (iterations) *iterations = iters;
+    if (final_residual) *final_residual = residual;
+    if (converged) *converged = conv;
+    if (l1_residual) *l1_residual = l1;
+    cleanup();
+    return rc;
+}
+
+}  // namespace b200
+
+// -------------------------------------------------------------------- pagerank --
+// API-compatible wrapper: result.ranks is a host new[] array (pagerank_free
+// deletes it).  adj must already be on the device; unlike the reference the
+// host arrays are not needed (the dangling scan runs on the device).
+PageRankResult pagerank(const CSRMatrix* adj_matrix, const PageRankConfig* config) {
+    PageRankResult result;
+    if (!adj_matrix) return result;
+    const int n = adj_matrix->num_rows;
+    result.ranks = new float[n > 0 ? n : 0];
+    if (n <= 0) return result;
+
+    const float init = 1.0f / n;
+    auto fill_initial = [&]() {  // what the reference returns when its first SpMV fails (:105-107, :135-150)
+        for (int i = 0; i < n; ++i) result.ranks[i] = init;
+        float sum = 0.0f;
+        for (int i = 0; i < n; ++i) sum += result.ranks[i];
+        if (sum > 0.0f)
+            for (int i = 0; i < n; ++i) result.ranks[i] /= sum;
+    };
+
+    float* d_ranks = nullptr;
+    if (cudaMalloc(&d_ranks, sizeof(float) * n) != cudaSuccess) throw CudaException(cudaGetLastError());
+    int iters = 0;
+    float residual = 0.0f;
+    bool conv = false;
+    const int rc = b200::pagerank_device(adj_matrix, config, d_ranks, &iters, &residual, &conv, nullptr);
+    if (rc != 0 && iters == 0) {
+        cudaFree(d_ranks);
+        fill_initial();
+        return result;
+    }
+    cudaError_t e = cudaMemcpy(result.ranks, d_ranks, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    cudaFree(d_ranks);
+    if (e != cudaSuccess) throw CudaException(e);
+    result.iterations = iters;
+    result.final_residual = residual;
+    result.converged = conv;
+    return result;
+}
+
+}  // namespace spmv

@@ -1,0 +1,327 @@
+/*
+ * spmv_b200.h -- C ABI of the B200-native SpMV library (libspmv_b200.so).
+ *
+ * This is the FFI boundary: extern "C", plain pointers and sizes, POD structs,
+ * int status codes, no C++ or torch types.  Every entry point is the C twin of
+ * one function of the LessUp/gpu-spmv C++ API and cites the reference
+ * declaration it replaces (paths relative to the reference repository).  The
+ * structs are layout-identical to the reference's (`spmv::CSRMatrix` ==
+ * `spmv_b200_csr`, ...), so a pointer obtained from the C++ surface
+ * (include/spmv_b200/api.hpp) can be passed here and vice versa.
+ *
+ * Conventions
+ *   - status: 0 or a negative spmv_b200_status (include/spmv/common.h:13-23).
+ *   - by-value C++ results (SpMVResult, PageRankResult, BenchmarkResult ...)
+ *     become out-parameters.
+ *   - nothing throws across this boundary.
+ *   - d_* / "device" pointers must be valid on the CURRENT CUDA device.
+ *   - there is no CPU fallback: device entry points fail with a CUDA status
+ *     when no sm_100 device is usable.
+ *
+ * Section E (extensions) is additive: stream-ordered calls, device-resident
+ * PageRank, row-sharded building blocks for one-process-per-GPU runs.
+ */
+#ifndef SPMV_B200_H
+#define SPMV_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPMV_B200_API __attribute__((visibility("default")))
+
+/* ---- status codes: include/spmv/common.h:13-23 ---- */
+typedef enum spmv_b200_status {
+    SPMV_B200_SUCCESS = 0,
+    SPMV_B200_INVALID_DIMENSION = -1,
+    SPMV_B200_CUDA_MALLOC = -2,
+    SPMV_B200_CUDA_MEMCPY = -3,
+    SPMV_B200_KERNEL_LAUNCH = -4,
+    SPMV_B200_INVALID_FORMAT = -5,
+    SPMV_B200_FILE_IO = -6,
+    SPMV_B200_OUT_OF_MEMORY = -7,
+    SPMV_B200_INVALID_ARGUMENT = -8
+} spmv_b200_status;
+
+/* include/spmv/common.h:26-39 */
+SPMV_B200_API const char* spmv_b200_error_string(int status);
+
+/* ---- POD structs ---- */
+
+/* include/spmv/csr_matrix.h:11-28 (72 bytes) */
+typedef struct spmv_b200_csr {
+    int num_rows, num_cols, nnz;
+    float* values;
+    int* col_indices;
+    int* row_ptrs;
+    float* d_values;
+    int* d_col_indices;
+    int* d_row_ptrs;
+    bool owns_host_memory;
+    bool owns_device_memory;
+} spmv_b200_csr;
+
+/* include/spmv/csr_matrix.h:64-69 */
+typedef struct spmv_b200_csr_stats {
+    float avg_nnz_per_row;
+    int max_nnz_per_row;
+    int min_nnz_per_row;
+    float skewness;
+} spmv_b200_csr_stats;
+
+/* include/spmv/ell_matrix.h:13-29 (56 bytes) */
+typedef struct spmv_b200_ell {
+    int num_rows, num_cols, max_nnz_per_row;
+    float* values;
+    int* col_indices;
+    float* d_values;
+    int* d_col_indices;
+    bool owns_host_memory;
+    bool owns_device_memory;
+} spmv_b200_ell;
+
+/* include/spmv/spmv.h:13-18 */
+enum {
+    SPMV_B200_SCALAR_CSR = 0,
+    SPMV_B200_VECTOR_CSR = 1,
+    SPMV_B200_MERGE_PATH = 2,
+    SPMV_B200_ELL_KERNEL = 3
+};
+
+/* include/spmv/spmv.h:11-24 (12 bytes) */
+typedef struct spmv_b200_config {
+    int kernel_type;
+    int block_size;
+    bool use_texture;
+} spmv_b200_config;
+
+/* include/spmv/spmv.h:27-36 (24 bytes) */
+typedef struct spmv_b200_result {
+    float* y;
+    float elapsed_ms;
+    float gflops;
+    float bandwidth_gb_s;
+    int error_code;
+} spmv_b200_result;
+
+/* include/spmv/bandwidth.h:10-18 */
+typedef struct spmv_b200_bandwidth {
+    float theoretical_bandwidth_gb_s;
+    float achieved_bandwidth_gb_s;
+    float efficiency;
+} spmv_b200_bandwidth;
+
+/* include/spmv/pagerank.h:9-15 */
+typedef struct spmv_b200_pagerank_config {
+    float damping_factor;
+    float tolerance;
+    int max_iterations;
+} spmv_b200_pagerank_config;
+
+/* include/spmv/pagerank.h:18-25 (24 bytes) */
+typedef struct spmv_b200_pagerank_result {
+    float* ranks;
+    int iterations;
+    float final_residual;
+    bool converged;
+} spmv_b200_pagerank_result;
+
+/* include/spmv/pagerank.h:35-38 */
+typedef struct spmv_b200_topk_node {
+    int node_id;
+    float rank;
+} spmv_b200_topk_node;
+
+/* include/spmv/benchmark.h:34-40 */
+typedef struct spmv_b200_bench_config {
+    int num_warmup_runs;
+    int num_runs;
+    bool compare_cpu;
+} spmv_b200_bench_config;
+
+/* C-safe image of include/spmv/benchmark.h:13-31 (std::string -> char[64]) */
+typedef struct spmv_b200_bench_result {
+    char name[64];
+    float execution_time_ms;
+    float gflops;
+    float bandwidth_gb_s;
+    float avg_time_ms;
+    float min_time_ms;
+    float max_time_ms;
+    float stddev_time_ms;
+    int num_runs;
+} spmv_b200_bench_result;
+
+/* ======================================================================= */
+/* A. CSR storage -- include/spmv/csr_matrix.h:31-71                        */
+/* ======================================================================= */
+SPMV_B200_API spmv_b200_csr* spmv_b200_csr_create(int rows, int cols, int nnz);          /* :31 */
+SPMV_B200_API void spmv_b200_csr_destroy(spmv_b200_csr* mat);                             /* :34 */
+SPMV_B200_API int spmv_b200_csr_from_dense(spmv_b200_csr* csr, const float* dense,
+                                           int rows, int cols);                          /* :39 */
+SPMV_B200_API int spmv_b200_csr_to_dense(const spmv_b200_csr* csr, float* dense);         /* :43 */
+SPMV_B200_API float spmv_b200_csr_get_element(const spmv_b200_csr* mat, int row, int col); /* :46 */
+SPMV_B200_API int spmv_b200_csr_to_gpu(spmv_b200_csr* mat);                               /* :49 */
+SPMV_B200_API int spmv_b200_csr_from_gpu(spmv_b200_csr* mat);                             /* :52 */
+SPMV_B200_API void spmv_b200_csr_free_gpu(spmv_b200_csr* mat);                            /* :55 */
+SPMV_B200_API int spmv_b200_csr_serialize(const spmv_b200_csr* mat, const char* filename);/* :58 */
+SPMV_B200_API int spmv_b200_csr_deserialize(spmv_b200_csr* mat, const char* filename);    /* :61 */
+SPMV_B200_API int spmv_b200_csr_compute_stats(const spmv_b200_csr* mat,
+                                              spmv_b200_csr_stats* out);                 /* :71 */
+
+/* ======================================================================= */
+/* B. ELL storage -- include/spmv/ell_matrix.h:31-66                        */
+/* ======================================================================= */
+SPMV_B200_API spmv_b200_ell* spmv_b200_ell_create(int rows, int cols, int max_nnz_per_row); /* :32 */
+SPMV_B200_API void spmv_b200_ell_destroy(spmv_b200_ell* mat);                              /* :35 */
+SPMV_B200_API int spmv_b200_ell_from_dense(spmv_b200_ell* ell, const float* dense,
+                                           int rows, int cols);                           /* :38 */
+SPMV_B200_API int spmv_b200_ell_from_csr(spmv_b200_ell* ell, const spmv_b200_csr* csr);    /* :41 */
+SPMV_B200_API int spmv_b200_ell_to_dense(const spmv_b200_ell* ell, float* dense);          /* :44 */
+SPMV_B200_API float spmv_b200_ell_get_element(const spmv_b200_ell* mat, int row, int col); /* :47 */
+SPMV_B200_API int spmv_b200_ell_to_gpu(spmv_b200_ell* mat);                                /* :50 */
+SPMV_B200_API int spmv_b200_ell_from_gpu(spmv_b200_ell* mat);                              /* :53 */
+SPMV_B200_API void spmv_b200_ell_free_gpu(spmv_b200_ell* mat);                             /* :56 */
+SPMV_B200_API int spmv_b200_ell_serialize(const spmv_b200_ell* mat, const char* filename); /* :59 */
+SPMV_B200_API int spmv_b200_ell_deserialize(spmv_b200_ell* mat, const char* filename);     /* :62 */
+SPMV_B200_API int spmv_b200_ell_index(int row, int k, int num_rows);                       /* :64-66 */
+
+/* ======================================================================= */
+/* C. SpMV + selector -- include/spmv/spmv.h:39-54                          */
+/* ======================================================================= */
+/* host reference functions of the API (never used by the device path) */
+SPMV_B200_API void spmv_b200_spmv_cpu_csr(const spmv_b200_csr* A, const float* x, float* y); /* :39 */
+SPMV_B200_API void spmv_b200_spmv_cpu_ell(const spmv_b200_ell* A, const float* x, float* y); /* :40 */
+
+/* device SpMV, blocking; config may be NULL (defaults {SCALAR_CSR,256,false});
+ * vec_size < 0 skips the dimension check.  Returns out->error_code. */
+SPMV_B200_API int spmv_b200_spmv_csr(const spmv_b200_csr* A, const float* d_x, float* d_y,
+                                     const spmv_b200_config* config, int vec_size,
+                                     spmv_b200_result* out);                              /* :43-44 */
+SPMV_B200_API int spmv_b200_spmv_ell(const spmv_b200_ell* A, const float* d_x, float* d_y,
+                                     const spmv_b200_config* config, int vec_size,
+                                     spmv_b200_result* out);                              /* :45-46 */
+SPMV_B200_API int spmv_b200_auto_config(const spmv_b200_csr* A, spmv_b200_config* out);    /* :49 */
+SPMV_B200_API bool spmv_b200_validate_dimensions(int num_cols, int vec_size);              /* :52-54 */
+
+/* ======================================================================= */
+/* D. Bandwidth model, PageRank, benchmark harness                          */
+/* ======================================================================= */
+SPMV_B200_API int spmv_b200_bandwidth_csr(const spmv_b200_csr* A, float elapsed_ms,
+                                          spmv_b200_bandwidth* out);   /* bandwidth.h:21 */
+SPMV_B200_API int spmv_b200_bandwidth_ell(const spmv_b200_ell* A, float elapsed_ms,
+                                          spmv_b200_bandwidth* out);   /* bandwidth.h:24 */
+SPMV_B200_API float spmv_b200_peak_bandwidth(void);                    /* bandwidth.h:27 */
+
+/* config may be NULL ({0.85, 1e-6, 100}).  out->ranks is a host array owned by
+ * the library; release with spmv_b200_pagerank_free. */
+SPMV_B200_API int spmv_b200_pagerank(const spmv_b200_csr* adj, const spmv_b200_pagerank_config* config,
+                                     spmv_b200_pagerank_result* out);  /* pagerank.h:29-32 */
+SPMV_B200_API void spmv_b200_pagerank_free(spmv_b200_pagerank_result* result); /* pagerank.h:35 */
+SPMV_B200_API int spmv_b200_pagerank_top_k(const spmv_b200_pagerank_result* result, int num_nodes,
+                                           int k, spmv_b200_topk_node* top_k); /* pagerank.h:43 */
+
+/* x is a HOST vector; A must already be on the device (benchmark.h:43-56) */
+SPMV_B200_API int spmv_b200_benchmark_csr(const spmv_b200_csr* A, const float* x,
+                                          const spmv_b200_config* config,
+                                          const spmv_b200_bench_config* bench_config,
+                                          spmv_b200_bench_result* out);          /* benchmark.h:43 */
+SPMV_B200_API int spmv_b200_benchmark_ell(const spmv_b200_ell* A, const float* x,
+                                          const spmv_b200_bench_config* bench_config,
+                                          spmv_b200_bench_result* out);          /* benchmark.h:51 */
+SPMV_B200_API int spmv_b200_compare_gpu_cpu_csr(const spmv_b200_csr* A, const float* x,
+                                                const spmv_b200_config* config,
+                                                const spmv_b200_bench_config* bench_config,
+                                                spmv_b200_bench_result* gpu_out,
+                                                spmv_b200_bench_result* cpu_out,
+                                                float* speedup);                 /* benchmark.h:66 */
+/* returns the JSON length (excluding NUL) or -1 when cap is too small */
+SPMV_B200_API int spmv_b200_benchmark_to_json(const spmv_b200_bench_result* result,
+                                              char* buf, int cap);               /* benchmark.h:74 */
+SPMV_B200_API int spmv_b200_benchmark_from_json(const char* json,
+                                                spmv_b200_bench_result* out);    /* benchmark.h:78 */
+
+/* ======================================================================= */
+/* E. Extensions (additive; nothing in the reference corresponds)           */
+/* ======================================================================= */
+
+SPMV_B200_API const char* spmv_b200_version(void);
+/* number of kernels this library has launched in this process so far */
+SPMV_B200_API unsigned long long spmv_b200_launch_count(void);
+/* the reference's selector decision without the B200 outlier override
+ * (src/spmv_cpu.cpp:34-50 verbatim); spmv_b200_auto_config == this unless the
+ * matrix has avg < 4 AND a row longer than 65536 nnz (then MERGE_PATH). */
+SPMV_B200_API int spmv_b200_reference_policy(const spmv_b200_csr* A, spmv_b200_config* out);
+
+/* stream-ordered SpMV: no sync, no timing.  stream is a cudaStream_t. */
+SPMV_B200_API int spmv_b200_spmv_csr_async(const spmv_b200_csr* A, const float* d_x, float* d_y,
+                                           const spmv_b200_config* config, void* stream);
+SPMV_B200_API int spmv_b200_spmv_ell_async(const spmv_b200_ell* A, const float* d_x, float* d_y,
+                                           void* stream);
+
+/* device-side ELL assembly from the DEVICE arrays of csr (ell_from_csr
+ * semantics, src/ell_matrix.cpp:111-159); fills ell's device arrays only
+ * (allocates them, sets owns_device_memory) and dims. */
+SPMV_B200_API int spmv_b200_ell_from_csr_device(spmv_b200_ell* ell, const spmv_b200_csr* csr);
+
+/* canonical merge-path coordinate of one diagonal (host; what the partition
+ * kernel computes per tile) and the nnz-balanced row split used for sharding */
+SPMV_B200_API int spmv_b200_merge_path_search(int diagonal, const int* row_ptrs, int num_rows,
+                                              int nnz, int* out_row, int* out_nz);
+SPMV_B200_API int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, int parts,
+                                           int* bounds /* [parts+1] */);
+
+/* ---- device-resident PageRank building blocks --------------------------- */
+
+/* Opaque plan over ONE row shard of an n_global x n_global column-normalised
+ * matrix: rows [row_offset, row_offset + shard->num_rows), global column ids,
+ * device arrays only.  Single GPU == one shard with row_offset 0. */
+typedef struct spmv_b200_pr_plan spmv_b200_pr_plan;
+
+SPMV_B200_API int spmv_b200_pr_plan_create(const spmv_b200_csr* shard, int row_offset,
+                                           int n_global, void* stream, spmv_b200_pr_plan** out);
+SPMV_B200_API void spmv_b200_pr_plan_destroy(spmv_b200_pr_plan* plan);
+
+/* d_colsum[c] += sum of this shard's values in column c (fp32 atomics) */
+SPMV_B200_API int spmv_b200_pr_colsum(const spmv_b200_pr_plan* plan, float* d_colsum, void* stream);
+/* d_bits[c/32] bit c%32 = (d_colsum[c] == 0.0f)  (dangling columns) */
+SPMV_B200_API int spmv_b200_pr_dangling_bits(const float* d_colsum, int n, uint32_t* d_bits,
+                                             void* stream);
+/* d_r[i] = 1.0f / n for the whole vector; d_dsum[0] = mass on dangling nodes */
+SPMV_B200_API int spmv_b200_pr_init(int n, const uint32_t* d_bits, float* d_r, float* d_dsum,
+                                    void* stream);
+/*
+ * One fused iteration on this shard (SpMV + damping/teleport + dangling
+ * contribution + residuals + next dangling mass in one pass):
+ *   r_new[row_offset + i] = (d * (A r_old)[i] + d * dsum / n) + (1 - d) / n
+ *   d_partial[0] += sum (r_new - r_old)^2   (f64)
+ *   d_partial[1] += sum |r_new - r_old|     (f64)
+ *   d_partial[2] += sum over dangling rows of r_new  (f64)
+ * d_r_old / d_r_new are FULL n_global-length vectors; d_dsum points to the
+ * dangling mass of r_old (fp32, device).  d_partial is overwritten with this
+ * shard's three sums (deterministic order).
+ */
+SPMV_B200_API int spmv_b200_pr_step(spmv_b200_pr_plan* plan, const float* d_r_old, float* d_r_new,
+                                    float damping, const float* d_dsum, const uint32_t* d_bits,
+                                    double* d_partial /* [3] */, void* stream);
+/* d_out[i] = d_r[i] / (float)sum(d_r) over n elements (f64 sum) */
+SPMV_B200_API int spmv_b200_pr_normalize(const float* d_r, int n, float* d_out, void* stream);
+
+/* whole loop on one GPU, ranks stay on the device (d_ranks [n]); the stop
+ * rule and result fields are those of pagerank() (src/pagerank.cu:93-150);
+ * l1_residual (optional) receives sum |r_new - r_old| of the last iteration */
+SPMV_B200_API int spmv_b200_pagerank_device(const spmv_b200_csr* adj,
+                                            const spmv_b200_pagerank_config* config,
+                                            float* d_ranks, int* iterations,
+                                            float* final_residual, bool* converged,
+                                            double* l1_residual);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* SPMV_B200_H */
