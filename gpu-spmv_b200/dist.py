@@ -1,0 +1,194 @@
+"""Row-sharded SpMV / PageRank for one process per GPU.
+
+The reference has no multi-GPU code; this is the additive
+extension BASELINE.json asks for: rows are split into contiguous nnz-balanced
+shards (spmv_b200_partition_rows), every rank keeps global column ids and a
+full-length rank vector, and one PageRank iteration is
+
+    local fused step (spmv_b200_pr_step: SpMV + damping/teleport + dangling +
+                      residual partial sums, one pass over the shard)
+    all-gather of the freshly written rank slices        (NCCL over NVLink)
+    all-reduce of {sum d^2, sum |d|, next dangling mass} (3 doubles)
+
+torch.distributed is plumbing only (rendezvous, NCCL communicator, streams);
+the arithmetic is in libspmv_b200.so.  The loop itself (`pagerank_loop`) is
+backend-agnostic so that the host logic -- partitioning, slice exchange,
+reduction of the partial sums, stop rule -- is covered by world_size-2 gloo
+tests on CPU with a checker-supplied local step.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import gpu_spmv_b200 as sp
+
+
+# ------------------------------------------------------------- partitioning ----
+
+def partition_rows(row_ptrs, parts):
+    """nnz-balanced contiguous row split; row_ptrs is a host int32 array or a
+    torch tensor (any device).  Returns a list of parts+1 row bounds."""
+    if torch.is_tensor(row_ptrs) and row_ptrs.is_cuda:
+        rows = row_ptrs.numel() - 1
+        nnz = int(row_ptrs[-1].item())
+        targets = torch.tensor([(nnz * p) // parts for p in range(1, parts)], dtype=row_ptrs.dtype,
+                               device=row_ptrs.device)
+        inner = torch.searchsorted(row_ptrs[:rows].contiguous(), targets, right=False).tolist() if parts > 1 else []
+        bounds = [0] + [int(b) for b in inner] + [rows]
+        for p in range(1, parts + 1):
+            bounds[p] = max(bounds[p], bounds[p - 1])
+        return bounds
+    rp = np.ascontiguousarray(row_ptrs.numpy() if torch.is_tensor(row_ptrs) else row_ptrs, dtype=np.int32)
+    return [int(b) for b in sp.partition_rows(rp, len(rp) - 1, parts)]
+
+
+def extract_shard(row_ptrs, col_indices, values, lo, hi):
+    """Rows [lo, hi) as a stand-alone CSR: row_ptrs rebased to 0, global column ids."""
+    a, b = int(row_ptrs[lo]), int(row_ptrs[hi])
+    rp = (row_ptrs[lo:hi + 1] - row_ptrs[lo]).contiguous()
+    return rp, col_indices[a:b].contiguous(), values[a:b].contiguous()
+
+
+# ------------------------------------------------------------ slice exchange ----
+
+def all_gather_slices(full, bounds, group=None):
+    """In-place all-gather of variable-length slices: on return every rank holds
+    full[bounds[p]:bounds[p+1]] as written by rank p."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    rank = dist.get_rank(group)
+    sizes = [bounds[p + 1] - bounds[p] for p in range(world)]
+    if len(set(sizes)) == 1 and sizes[0] > 0:
+        dist.all_gather_into_tensor(full[bounds[0]:bounds[world]], full[bounds[rank]:bounds[rank + 1]], group=group)
+        return
+    views = [full[bounds[p]:bounds[p + 1]] for p in range(world)]
+    if dist.get_backend(group) == "nccl" and all(s > 0 for s in sizes):
+        # uneven sizes: ProcessGroupNCCL runs this as one coalesced group of broadcasts
+        dist.all_gather(views, views[rank].clone(), group=group)
+        return
+    for p in range(world):
+        if sizes[p] > 0:
+            dist.broadcast(views[p], src=dist.get_global_rank(group, p) if group is not None else p, group=group)
+
+
+# ----------------------------------------------------------------- the loop ----
+
+class PageRankOutcome:
+    def __init__(self, ranks, iterations, final_residual, converged, l1_residual, seconds_per_iteration=None):
+        self.ranks, self.iterations, self.final_residual = ranks, iterations, final_residual
+        self.converged, self.l1_residual = converged, l1_residual
+        self.seconds_per_iteration = seconds_per_iteration
+
+
+def pagerank_loop(step, r_old, r_new, partial, bounds, damping, tolerance, max_iterations, group=None,
+                  fixed_iterations=0, on_iteration=None):
+    """The reference's iteration control (src/pagerank.cu:93-139) around a sharded step.
+
+    step(r_old, r_new, partial) must write this rank's slice of r_new and its
+    three partial sums (float64 tensor [3]: sum d^2, sum |d|, next dangling mass)
+    and is told the all-reduced dangling mass through step.set_dangling_mass().
+    Returns (final vector, iterations, residual, converged, l1)."""
+    iters, residual, l1, conv, from_new = 0, 0.0, 0.0, False, False
+    limit = fixed_iterations if fixed_iterations > 0 else max_iterations
+    for it in range(limit):
+        step(r_old, r_new, partial)
+        all_gather_slices(r_new, bounds, group)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+        step.set_dangling_mass(partial)
+        host = partial.cpu()
+        residual = float(np.sqrt(np.float32(host[0].item())))  # L2 norm of the delta in fp32 (src/pagerank.cu:118)
+        l1 = float(host[1].item())
+        iters = it + 1
+        if on_iteration is not None:
+            on_iteration(iters, residual)
+        if fixed_iterations <= 0 and residual < tolerance:
+            conv, from_new = True, True
+            break
+        if fixed_iterations > 0 and iters == limit:
+            conv, from_new = residual < tolerance, True
+            break
+        r_old, r_new = r_new, r_old
+    return (r_new if from_new else r_old), iters, residual, conv, l1
+
+
+# ------------------------------------------------------- CUDA step (product) ----
+
+class CudaShard:
+    """This rank's row shard on its GPU plus the fused-iteration plan."""
+
+    def __init__(self, n_global, row_lo, row_ptrs, col_indices, values, stream=None):
+        self.n = int(n_global)
+        self.row_lo = int(row_lo)
+        self.rows = row_ptrs.numel() - 1
+        self.dev = row_ptrs.device
+        self.csr = sp.DeviceCSR(self.rows, self.n, row_ptrs, col_indices, values)
+        self.stream = stream
+        handle = C.c_void_p()
+        rc = sp.lib.spmv_b200_pr_plan_create(self.csr.ptr, self.row_lo, self.n, self._s(), C.byref(handle))
+        if rc != 0:
+            raise RuntimeError(f"pr_plan_create: {sp.spmv_error_string(rc)}")
+        self.plan = handle
+        self.bits = torch.zeros((self.n + 31) // 32, dtype=torch.int32, device=self.dev)
+        self.dsum = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.damping = 0.85
+
+    def _s(self):
+        return C.c_void_p(self.stream if self.stream is not None else torch.cuda.current_stream().cuda_stream)
+
+    def close(self):
+        if self.plan:
+            sp.lib.spmv_b200_pr_plan_destroy(self.plan)
+            self.plan = None
+
+    def setup_dangling(self, group=None):
+        """Dangling columns = global column sums equal to 0 (src/pagerank.cu:20-48)."""
+        colsum = torch.zeros(self.n, dtype=torch.float32, device=self.dev)
+        rc = sp.lib.spmv_b200_pr_colsum(self.plan, sp.dptr(colsum), self._s())
+        assert rc == 0
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
+        rc = sp.lib.spmv_b200_pr_dangling_bits(sp.dptr(colsum), self.n, sp.dptr(self.bits), self._s())
+        assert rc == 0
+
+    def init_vector(self, r):
+        rc = sp.lib.spmv_b200_pr_init(self.n, sp.dptr(self.bits), sp.dptr(r), sp.dptr(self.dsum), self._s())
+        assert rc == 0
+
+    def __call__(self, r_old, r_new, partial):
+        rc = sp.lib.spmv_b200_pr_step(self.plan, sp.dptr(r_old), sp.dptr(r_new), self.damping, sp.dptr(self.dsum),
+                                      sp.dptr(self.bits), sp.dptr(partial), self._s())
+        if rc != 0:
+            raise RuntimeError(f"pr_step: {sp.spmv_error_string(rc)}")
+
+    def set_dangling_mass(self, partial):
+        self.dsum.copy_(partial[2:3].to(torch.float32))
+
+    def normalize(self, r):
+        out = torch.empty_like(r)
+        rc = sp.lib.spmv_b200_pr_normalize(sp.dptr(r), self.n, sp.dptr(out), self._s())
+        assert rc == 0
+        return out
+
+    def spmv(self, x, y_full, kernel=sp.MERGE_PATH):
+        """y_full[row_lo : row_lo + rows] = A_shard x (no collective: x is replicated)."""
+        y = y_full[self.row_lo:self.row_lo + self.rows]
+        return sp.spmv_csr_async(self.csr.ptr, x, y, sp.make_config(kernel), self._s().value or 0)
+
+
+def pagerank_sharded(shard, bounds, damping=0.85, tolerance=1e-6, max_iterations=100, group=None,
+                     fixed_iterations=0):
+    """PageRank over row shards, one CudaShard per rank; returns a PageRankOutcome whose
+    ranks tensor (full length, normalised) is identical on every rank."""
+    shard.damping = float(damping)
+    shard.setup_dangling(group)
+    r_a = torch.empty(shard.n, dtype=torch.float32, device=shard.dev)
+    r_b = torch.empty_like(r_a)
+    partial = torch.zeros(3, dtype=torch.float64, device=shard.dev)
+    shard.init_vector(r_a)
+    fin, iters, residual, conv, l1 = pagerank_loop(shard, r_a, r_b, partial, bounds, damping, tolerance,
+                                                    max_iterations, group, fixed_iterations)
+    return PageRankOutcome(shard.normalize(fin), iters, residual, conv, l1)

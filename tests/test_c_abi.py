@@ -1,0 +1,125 @@
+"""The C-ABI library loads, exports every symbol include/spmv_b200.h declares
+and the 39 C++ symbols of the reference API; the product
+never routes through the oracle; device entry points fail loudly without a GPU."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "gpu-spmv_b200", "lib", "libspmv_b200.so")
+
+APPENDIX_A = """
+_ZN4spmv10csr_createEiii _ZN4spmv10ell_createEiii _ZN4spmv11csr_destroyEPNS_9CSRMatrixE
+_ZN4spmv11ell_destroyEPNS_9ELLMatrixE _ZN4spmv14csr_from_denseEPNS_9CSRMatrixEPKfii
+_ZN4spmv14ell_from_denseEPNS_9ELLMatrixEPKfii _ZN4spmv12csr_to_denseEPKNS_9CSRMatrixEPf
+_ZN4spmv12ell_to_denseEPKNS_9ELLMatrixEPf _ZN4spmv15csr_get_elementEPKNS_9CSRMatrixEii
+_ZN4spmv15ell_get_elementEPKNS_9ELLMatrixEii _ZN4spmv10csr_to_gpuEPNS_9CSRMatrixE
+_ZN4spmv10ell_to_gpuEPNS_9ELLMatrixE _ZN4spmv12csr_from_gpuEPNS_9CSRMatrixE
+_ZN4spmv12ell_from_gpuEPNS_9ELLMatrixE _ZN4spmv12csr_free_gpuEPNS_9CSRMatrixE
+_ZN4spmv12ell_free_gpuEPNS_9ELLMatrixE _ZN4spmv13csr_serializeEPKNS_9CSRMatrixEPKc
+_ZN4spmv13ell_serializeEPKNS_9ELLMatrixEPKc _ZN4spmv15csr_deserializeEPNS_9CSRMatrixEPKc
+_ZN4spmv15ell_deserializeEPNS_9ELLMatrixEPKc _ZN4spmv17csr_compute_statsEPKNS_9CSRMatrixE
+_ZN4spmv12ell_from_csrEPNS_9ELLMatrixEPKNS_9CSRMatrixE _ZN4spmv12spmv_cpu_csrEPKNS_9CSRMatrixEPKfPf
+_ZN4spmv12spmv_cpu_ellEPKNS_9ELLMatrixEPKfPf _ZN4spmv16spmv_auto_configEPKNS_9CSRMatrixE
+_ZN4spmv8spmv_csrEPKNS_9CSRMatrixEPKfPfPKNS_10SpMVConfigEi
+_ZN4spmv8spmv_ellEPKNS_9ELLMatrixEPKfPfPKNS_10SpMVConfigEi
+_ZN4spmv21compute_bandwidth_csrEPKNS_9CSRMatrixEf _ZN4spmv21compute_bandwidth_ellEPKNS_9ELLMatrixEf
+_ZN4spmv22get_gpu_peak_bandwidthEv _ZN4spmv8pagerankEPKNS_9CSRMatrixEPKNS_14PageRankConfigE
+_ZN4spmv13pagerank_freeEPNS_14PageRankResultE
+_ZN4spmv14pagerank_top_kEPKNS_14PageRankResultEiiPNS_8TopKNodeE
+_ZN4spmv13benchmark_csrEPKNS_9CSRMatrixEPKfPKNS_10SpMVConfigEPKNS_15BenchmarkConfigE
+_ZN4spmv13benchmark_ellEPKNS_9ELLMatrixEPKfPKNS_15BenchmarkConfigE
+_ZN4spmv19compare_gpu_cpu_csrEPKNS_9CSRMatrixEPKfPKNS_10SpMVConfigEPKNS_15BenchmarkConfigE
+_ZN4spmv17benchmark_to_jsonB5cxx11ERKNS_15BenchmarkResultE
+_ZN4spmv18comparison_to_jsonB5cxx11ERKNS_16ComparisonResultE
+_ZN4spmv19benchmark_from_jsonERKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEE
+""".split()
+
+
+def exported():
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB], text=True)
+    return {line.split()[-1] for line in out.splitlines() if line.strip()}
+
+
+def test_every_declared_symbol_is_exported(sp):
+    header = open(os.path.join(ROOT, "include", "spmv_b200.h")).read()
+    declared = set(re.findall(r"SPMV_B200_API[^;(]*?\b(spmv_b200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 55
+    syms = exported()
+    assert not (declared - syms), sorted(declared - syms)
+    from gpu_spmv_b200 import capi
+    assert declared == set(capi.PROTOTYPES), declared ^ set(capi.PROTOTYPES)
+
+
+def test_reference_cxx_symbols_exported(sp):
+    assert len(APPENDIX_A) == 39  # SURVEY Appendix A lists 39 mangled names
+    syms = exported()
+    assert not [s for s in APPENDIX_A if s not in syms]
+
+
+def test_struct_sizes_match_reference_layout(sp):
+    import ctypes as C
+    sizes = {sp.CSRMatrix: 72, sp.ELLMatrix: 56, sp.SpMVConfig: 12, sp.SpMVResult: 24, sp.CSRStats: 16,
+             sp.PageRankConfig: 12, sp.PageRankResult: 24, sp.TopKNode: 8, sp.BandwidthMetrics: 12,
+             sp.BenchmarkConfig: 12}
+    for t, n in sizes.items():
+        assert C.sizeof(t) == n, t
+    assert sp.CSRMatrix.values.offset == 16 and sp.CSRMatrix.d_values.offset == 40
+    assert sp.CSRMatrix.owns_host_memory.offset == 64 and sp.CSRMatrix.owns_device_memory.offset == 65
+    assert sp.ELLMatrix.d_values.offset == 32 and sp.ELLMatrix.owns_host_memory.offset == 48
+    assert sp.SpMVResult.error_code.offset == 20 and sp.PageRankResult.converged.offset == 16
+
+
+def test_product_never_touches_the_oracle():
+    """No file of the product (package, include/) names oracle/ code."""
+    bad = []
+    for base in ("gpu-spmv_b200", "include"):
+        for dirpath, _dirs, files in os.walk(os.path.join(ROOT, base)):
+            if os.sep + "build" in dirpath or os.sep + "lib" in dirpath or "__pycache__" in dirpath:
+                continue
+            for f in files:
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"liboracle|oracle_binding|spmv_oracle|libspmv_ref|orc_[a-z_]+\(|ref_shim", text):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+    deps = subprocess.check_output(["ldd", LIB], text=True)
+    assert "oracle" not in deps and "spmv_ref" not in deps
+
+
+def test_argument_validation_order(sp):
+    # reference src/spmv_kernels.cu:219-232: null -> -8, dimension -> -1, missing device arrays -> -5
+    A = sp.csr_create(3, 4, 0)
+    assert sp.spmv_csr(None, 1, 1, None, -1).error_code == -8
+    assert sp.spmv_csr(A, None, 1, None, -1).error_code == -8
+    assert sp.spmv_csr(A, 1, None, None, -1).error_code == -8
+    assert sp.spmv_csr(A, 1, 1, None, 3).error_code == -1
+    assert sp.spmv_csr(A, 1, 1, None, 4).error_code == -5   # not on the device
+    assert sp.spmv_csr(A, 1, 1, None, -1).error_code == -5  # vec_size < 0 skips the dimension check
+    sp.csr_destroy(A)
+    E = sp.ell_create(3, 4, 2)
+    assert sp.spmv_ell(None, 1, 1, None, -1).error_code == -8
+    assert sp.spmv_ell(E, 1, 1, None, 5).error_code == -1
+    assert sp.spmv_ell(E, 1, 1, None, 4).error_code == -5
+    sp.ell_destroy(E)
+    assert sp.spmv_validate_dimensions(4, 4) and not sp.spmv_validate_dimensions(4, 5)
+
+
+def test_device_entry_points_fail_loudly_without_gpu(sp):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    A = sp.csr_create(0, 0, 0)
+    sp.csr_from_dense(A, np.eye(4, dtype=np.float32), 4, 4)
+    assert sp.csr_to_gpu(A) != 0  # CUDA failure is reported, nothing is emulated on the host
+    assert not A.contents.d_values
+    A.contents.d_row_ptrs = 16
+    A.contents.d_col_indices = 16
+    A.contents.d_values = 16  # pretend device arrays: the call must still fail, not compute on the CPU
+    assert sp.spmv_csr(A, 16, 16, None, 4).error_code != 0
+    A.contents.d_row_ptrs = None
+    A.contents.d_col_indices = None
+    A.contents.d_values = None
+    sp.csr_destroy(A)

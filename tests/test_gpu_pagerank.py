@@ -1,0 +1,174 @@
+"""Parity of the fused PageRank iteration with the reference recurrence
+(src/pagerank.cu:50-153) through the C ABI.  north_star: rank vectors within
+an L1 distance of 1e-6, identical top-k up to ties."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def gen_mod():
+    import gpu_spmv_b200.gen as gen
+    return gen
+
+
+def gpu_pagerank(sp, n, rp, ci, va, damping=0.85, tol=1e-6, max_it=100):
+    G = sp.csr_from_arrays(n, n, rp, ci, va)
+    assert sp.csr_to_gpu(G) == 0
+    res, ranks = sp.pagerank(G, sp.make_pagerank_config(damping, tol, max_it))
+    out = (ranks, res.iterations, res.final_residual, bool(res.converged))
+    sp.pagerank_free(res)
+    assert not res.ranks  # pagerank_free nulls the pointer and is idempotent
+    sp.pagerank_free(res)
+    sp.csr_destroy(G)
+    return out
+
+
+def same_top_k_up_to_ties(ranks_a, ranks_b, k, tol=1e-7):
+    """Top-k sets may differ only in members whose ranks are within tol of the k-th rank."""
+    k = min(k, len(ranks_a))
+    top_a, top_b = np.argsort(-ranks_a, kind="stable")[:k], np.argsort(-ranks_b, kind="stable")[:k]
+    kth = ranks_a[top_a[-1]]
+    for i in set(top_a.tolist()) ^ set(top_b.tolist()):
+        assert abs(ranks_a[i] - kth) <= tol and abs(ranks_b[i] - kth) <= tol, i
+    assert np.all(np.abs(np.sort(ranks_a[top_a]) - np.sort(ranks_b[top_b])) <= tol)
+
+
+def test_reference_property_inputs(sp, orc, cuda, golden):
+    """Inputs of PageRankPropertyTest.ScoreInvariants (tests/test_pagerank.cu:18-77): the
+    reference's invariants, then the values against the literal fp32 restatement."""
+    g = golden.pr
+    for it in range(int(g["n_cases"][0])):
+        p = f"p{it}_"
+        n = int(g[p + "n"][0])
+        rp, ci, va = g[p + "row_ptrs"], g[p + "col_indices"], g[p + "values"]
+        ranks, iters, res, conv = gpu_pagerank(sp, n, rp, ci, va, 0.85, 1e-5, 50)
+        assert np.all(ranks >= 0) and abs(float(ranks.sum(dtype=np.float64)) - 1.0) < 1e-4
+        assert conv or iters == 50
+        if conv:
+            assert res < 1e-5
+        o_ranks, o_it, o_res, o_conv = orc.pagerank_f32(n, n, rp, ci, va, 0.85, 1e-5, 50)
+        assert abs(iters - o_it) <= 1 and conv == o_conv
+        o_same, _, _, _, _ = orc.pagerank_f64(n, n, rp, ci, va, 0.85, 1e-5, 50, fixed_it=iters)
+        assert np.abs(ranks.astype(np.float64) - o_same).sum() <= 1e-6
+        assert np.abs(ranks.astype(np.float64) - o_ranks).sum() <= 1e-5  # <= one iteration apart near the threshold
+        same_top_k_up_to_ties(ranks, o_same, 5)
+
+
+def test_reference_unit_cases(sp, orc, cuda):
+    # 3-cycle (tests/test_pagerank.cu:140-164): converged, equal ranks
+    rp, ci, va = orc.csr_from_dense(np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0]], np.float32))
+    ranks, iters, res, conv = gpu_pagerank(sp, 3, rp, ci, va)
+    assert conv and np.allclose(ranks, 1 / 3, atol=1e-4)
+    # 4-node symmetric graph, top-2 (tests/test_pagerank.cu:166-189)
+    adj = np.array([[0, 1, 1, 0], [1, 0, 1, 1], [1, 1, 0, 1], [0, 1, 1, 0]], np.float32)
+    adj = adj / adj.sum(axis=0, keepdims=True)
+    rp, ci, va = orc.csr_from_dense(adj)
+    ranks, _, _, _ = gpu_pagerank(sp, 4, rp, ci, va)
+    ids, vals = sp.pagerank_top_k(ranks, 2)
+    assert set(ids.tolist()) == {1, 2} and vals[0] >= vals[1]
+    # graph with dangling nodes and isolated rows; not on the device -> normalised initial vector (src/pagerank.cu:105-107)
+    G = sp.csr_from_arrays(3, 3, rp[:4] * 0, [], [])
+    res, r = sp.pagerank(G, None)
+    assert res.iterations == 0 and not res.converged and np.allclose(r, 1 / 3)
+    sp.pagerank_free(res)
+    sp.csr_destroy(G)
+    res, r = sp.pagerank(None, None)
+    assert r is None and res.iterations == 0
+
+
+@pytest.mark.parametrize("scale,edge_factor,seed", [(8, 4, 1), (12, 8, 2), (15, 16, 3), (17, 16, 4)])
+def test_rmat_graphs_vs_restatement(sp, orc, cuda, scale, edge_factor, seed):
+    """R-MAT graphs (dangling nodes, empty rows, hub rows spanning many merge tiles)."""
+    gen = gen_mod()
+    n, rp, ci, va = gen.rmat_pagerank_csr(scale, edge_factor, seed, "cpu")
+    rp, ci, va = rp.numpy(), ci.numpy(), va.numpy()
+    n_dangling, _ = orc.find_dangling(n, n, rp, ci, va)
+    assert n_dangling > 0
+    ranks, iters, res, conv = gpu_pagerank(sp, n, rp, ci, va, 0.85, 1e-6, 100)
+    assert conv and res < 1e-6
+    o_ranks, o_it, o_l2, o_l1, o_conv = orc.pagerank_f64(n, n, rp, ci, va, 0.85, 1e-6, 100)
+    assert abs(iters - o_it) <= 1
+    o_same, _, l2_same, l1_same, _ = orc.pagerank_f64(n, n, rp, ci, va, 0.85, 1e-6, 100, fixed_it=iters)
+    assert np.abs(ranks.astype(np.float64) - o_same).sum() <= 1e-6
+    assert abs(res - l2_same) <= 1e-8 + 1e-3 * l2_same
+    assert abs(float(ranks.sum(dtype=np.float64)) - 1.0) < 1e-5
+    same_top_k_up_to_ties(ranks, o_same, 20)
+    if n <= 1 << 15:  # literal fp32 reference recurrence is trustworthy at this size
+        l_ranks, l_it, _, _ = orc.pagerank_f32(n, n, rp, ci, va, 0.85, 1e-6, 100)
+        assert abs(l_it - iters) <= 1 and np.abs(ranks.astype(np.float64) - l_ranks).sum() <= 2e-6
+
+
+def test_device_resident_api_and_shards_on_one_gpu(sp, orc, cuda):
+    """spmv_b200_pagerank_device and the sharded building blocks: three row shards stepped
+    one after another on one GPU must reproduce the unsharded iteration."""
+    gen = gen_mod()
+    import gpu_spmv_b200.dist as D
+    n, rp, ci, va = gen.rmat_pagerank_csr(14, 16, 5, cuda)
+    G = sp.DeviceCSR(n, n, rp, ci, va)
+    d_ranks = torch.empty(n, device=cuda)
+    rc, iters, res, conv, l1 = sp.pagerank_device(G.ptr, d_ranks, sp.make_pagerank_config(0.85, 1e-6, 100))
+    assert rc == 0 and conv and l1 > 0
+    o_same, _, l2, o_l1, _ = orc.pagerank_f64(n, n, rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy(), 0.85, 1e-6,
+                                               100, fixed_it=iters)
+    assert np.abs(d_ranks.cpu().numpy().astype(np.float64) - o_same).sum() <= 1e-6
+    assert abs(l1 - o_l1) <= 1e-3 * o_l1 + 1e-9
+
+    bounds = D.partition_rows(rp, 3)
+    assert bounds == D.partition_rows(rp.cpu(), 3) == orc.partition_rows(n, rp.cpu().numpy(), 3).tolist()
+    shards = []
+    for p in range(3):
+        srp, sci, sva = D.extract_shard(rp, ci, va, bounds[p], bounds[p + 1])
+        shards.append(D.CudaShard(n, bounds[p], srp, sci, sva))
+    for s in shards:
+        s.setup_dangling()
+    # every shard contributes its own column sums; emulate the all-reduce by summing bits' sources
+    colsum = torch.zeros(n, device=cuda)
+    for s in shards:
+        assert sp.lib.spmv_b200_pr_colsum(s.plan, sp.dptr(colsum), None) == 0
+    for s in shards:
+        assert sp.lib.spmv_b200_pr_dangling_bits(sp.dptr(colsum), n, sp.dptr(s.bits), None) == 0
+    r_old, r_new = torch.empty(n, device=cuda), torch.empty(n, device=cuda)
+    shards[0].init_vector(r_old)
+    dsum0 = shards[0].dsum.clone()
+    total = torch.zeros(3, dtype=torch.float64, device=cuda)
+    part = torch.zeros(3, dtype=torch.float64, device=cuda)
+    for it in range(iters):
+        total.zero_()
+        for s in shards:
+            s.dsum.copy_(dsum0)
+            s(r_old, r_new, part)
+            total += part
+        dsum0 = total[2:3].to(torch.float32)
+        r_old, r_new = r_new, r_old
+    final = shards[0].normalize(r_old)
+    assert np.abs(final.cpu().numpy().astype(np.float64) - o_same).sum() <= 1e-6
+    assert abs(float(torch.sqrt(total[0].float())) - res) <= 1e-3 * res + 1e-9
+    for s in shards:
+        s.close()
+
+
+def test_reference_cuda_pagerank_agrees(sp, orc, ref, cuda):
+    """Secondary oracle: the reference's own pagerank() (GPU SpMV + host loops) compiled for
+    sm_100a from the unmodified sources, where it is trustworthy (n <= 2^15)."""
+    gen = gen_mod()
+    n, rp, ci, va = gen.rmat_pagerank_csr(13, 8, 6, "cpu")
+    rp, ci, va = rp.numpy(), ci.numpy(), va.numpy()
+    h, keep = ref.csr_wrap(n, n, rp, ci, va)
+    assert ref.L.ref_csr_to_gpu(h) == 0
+    r_ref = np.empty(n, np.float32)
+    res, conv = C.c_float(0), C.c_int(0)
+    it_ref = ref.L.ref_pagerank(h, 0.85, 1e-6, 100, r_ref.ctypes.data_as(C.POINTER(C.c_float)), C.byref(res),
+                                C.byref(conv))
+    ranks, iters, my_res, my_conv = gpu_pagerank(sp, n, rp, ci, va)
+    assert bool(conv.value) == my_conv and abs(it_ref - iters) <= 1
+    assert np.abs(ranks.astype(np.float64) - r_ref).sum() <= 2e-6
+    same_top_k_up_to_ties(ranks, r_ref, 10, tol=2e-7)
+    ids, vals = sp.pagerank_top_k(ranks, 10)
+    rid, rv = np.empty(10, np.int32), np.empty(10, np.float32)
+    ref.L.ref_pagerank_top_k(ranks.ctypes.data_as(C.POINTER(C.c_float)), n, 10, rid.ctypes.data_as(C.POINTER(C.c_int)),
+                             rv.ctypes.data_as(C.POINTER(C.c_float)))
+    assert np.array_equal(vals, rv)  # same ranks position by position (ids may differ only on ties)
