@@ -194,6 +194,7 @@ def timed_region(torch, stream, fn, steps, dist_on):
 
 
 def bench_kernel(torch, sp, stream, launch, bytes_per_launch, steps, warmup, dist_on=False, world=1):
+    torch.cuda.synchronize()  # inputs were produced on torch's default stream; `stream` does not wait for it
     for _ in range(max(warmup, 3)):
         launch()
     torch.cuda.synchronize()
@@ -273,7 +274,12 @@ def run_product_arm(args):
     s_ptr = stream.cuda_stream
     extra = {}
 
+    def log(msg):
+        if rank == 0:
+            print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
     # ---- headline: config 2, ELL, one 16.7 M-row band per rank (weak scaling) -----------------
+    log("config 2: build + ELL headline")
     n_loc = GRID * GRID
     grid_y = GRID * world
     n_cols = GRID * grid_y
@@ -291,6 +297,7 @@ def run_product_arm(args):
         rc = sp.lib.spmv_b200_spmv_ell_async(E, sp.dptr(x), sp.dptr(y), C.c_void_p(s_ptr))
         assert rc == 0
 
+    torch.cuda.synchronize()  # x / matrix were produced on the default stream; `stream` does not wait for it
     for _ in range(max(args.warmup, 3)):
         ell_step()
     torch.cuda.synchronize()
@@ -308,6 +315,7 @@ def run_product_arm(args):
     launch_gbs = ell_bytes / (ms_per_step * 1e-3) / 1e9
 
     # ---- e2e: blocking C-ABI call with host x / y (pinned), copies inside the timed region -----
+    log("e2e")
     x_host = x.cpu().pin_memory()
     y_host = torch.empty(n_loc, dtype=torch.float32).pin_memory()
     res = sp.SpMVResult()
@@ -340,6 +348,7 @@ def run_product_arm(args):
            "api": "spmv_b200_spmv_ell (blocking C ABI) + pinned H2D of x + D2H of y"}
 
     # ---- CPU baseline (rank 0, N = 1): the reference's spmv_cpu_ell on the same matrix ---------
+    log("cpu baseline")
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         reps = 3
@@ -351,6 +360,7 @@ def run_product_arm(args):
                                   "(single-threaded: the reference has no threading)"}
 
     # ---- extra: the CSR kernels on config 2 -----------------------------------------------------
+    log("config 2: CSR kernels")
     if not args.quick:
         for kernel, name in ((sp.VECTOR_CSR, "csr_vector"), (sp.SCALAR_CSR, "csr_scalar"), (sp.MERGE_PATH, "csr_merge")):
             cfg = sp.make_config(kernel)
@@ -365,6 +375,7 @@ def run_product_arm(args):
 
     if not args.quick and world == 1:
         # ---- config 3: short rows + 4 outlier rows of 1 M nnz: scalar (reference policy) vs merge ---
+        log("config 3")
         rows3 = args.c3_rows
         rp3, ci3, va3 = gen.short_rows_with_outliers_csr(rows3, 43, dev)
         A3 = sp.DeviceCSR(rows3, rows3, rp3, ci3, va3)
@@ -382,9 +393,11 @@ def run_product_arm(args):
         torch.cuda.empty_cache()
 
     # ---- config 4 / 5: R-MAT SpMV (merge-path) and PageRank, row-sharded over the ranks -----------
+    log("R-MAT build + SpMV")
     if not args.quick:
         scale = args.rmat_scale
         n, bounds, srp, sci, sva, n_edges = build_rmat_shard(torch, gen, scale, 16, 44, rank, world, dev)
+        torch.cuda.synchronize()
         shard = D.CudaShard(n, bounds[rank], srp, sci, sva, stream=s_ptr)
         xg = torch.full((n,), 1.0 / n, dtype=torch.float32, device=dev)
         yg = torch.empty(n, dtype=torch.float32, device=dev)
@@ -400,6 +413,7 @@ def run_product_arm(args):
                                             "frac_of_8000": gbs / world / 8000.0, "bytes_all_ranks": float(tot4.item()),
                                             "nnz": n_edges, "rows": n}
         # PageRank: fixed number of iterations of the sharded loop, device-timed, max over ranks
+        log("PageRank")
         shard.damping = 0.85
         with torch.cuda.stream(stream):
             shard.setup_dangling()

@@ -199,9 +199,10 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
 
     // ---- stage products of non-zeros [nz_s, nz_e) at slot (j - base) ----------
     const int base = nz_s & ~3;
+    const bool vec_ok = dev::aligned16(values) && dev::aligned16(col_indices);  // any device pointer is legal
     for (int j = base + 4 * tid; j < nz_e; j += 4 * kT) {
         float p0, p1, p2, p3;
-        if (j >= nz_s && j + 4 <= nz_e) {
+        if (vec_ok && j >= nz_s && j + 4 <= nz_e) {
             const float4 v = dev::ld_stream_f4(values + j);
             const int4 c = dev::ld_stream_i4(col_indices + j);
             p0 = v.x * dev::ld_x(x + c.x);

@@ -101,7 +101,10 @@ csr_stream_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
 
     // ---- passes over the window's non-zero range ----------------------------
     // `base` is 4-aligned so that 128-bit loads of values/col_indices are
-    // aligned; slot (j - base) of s_prod holds the product of non-zero j.
+    // aligned (when the arrays themselves are 16-byte aligned; any device
+    // pointer is legal in the public struct, so that is checked here); slot
+    // (j - base) of s_prod holds the product of non-zero j.
+    const bool vec_ok = dev::aligned16(values) && dev::aligned16(col_indices);
     for (int base = n0 & ~3; base < n1; base += kProductCap) {
         const int hi = min(base + kProductCap, n1);  // exclusive end of this pass
         const int lo = max(base, n0);
@@ -109,7 +112,7 @@ csr_stream_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
 
         for (int j = base + 4 * tid; j < hi; j += 4 * kThreads) {
             float p0, p1, p2, p3;
-            if (j >= lo && j + 4 <= hi) {
+            if (vec_ok && j >= lo && j + 4 <= hi) {
                 const float4 v = dev::ld_stream_f4(values + j);
                 const int4 c = dev::ld_stream_i4(col_indices + j);
                 p0 = __fmul_rn(v.x, dev::ld_x(x + c.x));
@@ -161,10 +164,11 @@ csr_warp_row_kernel(int rows, const int* __restrict__ row_ptrs, const int* __res
     if (warp >= rows) return;
     const int a = row_ptrs[warp];
     const int b = row_ptrs[warp + 1];
+    const bool vec_ok = dev::aligned16(values) && dev::aligned16(col_indices);
     float s = 0.0f;
     // 4-element groups starting at the aligned address at or below `a`
     for (int j = (a & ~3) + 4 * lane; j < b; j += 128) {
-        if (j >= a && j + 4 <= b) {
+        if (vec_ok && j >= a && j + 4 <= b) {
             const float4 v = dev::ld_stream_f4(values + j);
             const int4 c = dev::ld_stream_i4(col_indices + j);
             s = fmaf(v.x, dev::ld_x(x + c.x), s);

@@ -93,9 +93,10 @@ int pr_step(PrPlan* p, const float* d_r_old, float* d_r_new, float damping, cons
 const CsrView& pr_plan_view(const PrPlan* p) { return p->A; }
 double* pr_plan_tmp(PrPlan* p) { return p->tmp; }
 
-// The whole loop on one device; d_ranks receives the normalised ranks.
+// The whole loop on one device; d_ranks receives the ranks, normalised on the device with an
+// f64 sum when `normalize` is set, else the raw final iterate.
 int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,
-                    float* final_residual, bool* converged, double* l1_residual) {
+                    float* final_residual, bool* converged, double* l1_residual, bool normalize) {
     if (!adj || !d_ranks) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     PageRankConfig defaults;
     if (!config) config = &defaults;
@@ -172,7 +173,8 @@ int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d
     }
     // final vector (:135-139) and normalisation (:142-150)
     const float* fin = from_new ? r_new : r_old;
-    launch_normalize(fin, n, d_ranks, plan->tmp, stream);
+    if (normalize) launch_normalize(fin, n, d_ranks, plan->tmp, stream);
+    else cudaMemcpyAsync(d_ranks, fin, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream);
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -213,7 +215,13 @@ PageRankResult pagerank(const CSRMatrix* adj_matrix, const PageRankConfig* confi
     int iters = 0;
     float residual = 0.0f;
     bool conv = false;
-    const int rc = b200::pagerank_device(adj_matrix, config, d_ranks, &iters, &residual, &conv, nullptr);
+    // Up to 2^24 nodes the final normalisation is the reference's own host code (sequential fp32
+    // sum, :142-150) on the un-normalised vector, so the returned ranks carry the same rounding as
+    // the reference's; beyond that its fp32 sum is meaningless (0.25 at n = 2^26) and the
+    // f64 device normalisation is used.
+    const bool literal_normalisation = n <= (1 << 24);
+    const int rc = b200::pagerank_device(adj_matrix, config, d_ranks, &iters, &residual, &conv, nullptr,
+                                         !literal_normalisation);
     if (rc != 0 && iters == 0) {
         cudaFree(d_ranks);
         fill_initial();
@@ -222,6 +230,12 @@ PageRankResult pagerank(const CSRMatrix* adj_matrix, const PageRankConfig* confi
     cudaError_t e = cudaMemcpy(result.ranks, d_ranks, sizeof(float) * n, cudaMemcpyDeviceToHost);
     cudaFree(d_ranks);
     if (e != cudaSuccess) throw CudaException(e);
+    if (literal_normalisation) {
+        float sum = 0.0f;
+        for (int i = 0; i < n; ++i) sum += result.ranks[i];
+        if (sum > 0.0f)
+            for (int i = 0; i < n; ++i) result.ranks[i] /= sum;
+    }
     result.iterations = iters;
     result.final_residual = residual;
     result.converged = conv;

@@ -56,6 +56,8 @@ def extract_shard(row_ptrs, col_indices, values, lo, hi):
 def all_gather_slices(full, bounds, group=None):
     """In-place all-gather of variable-length slices: on return every rank holds
     full[bounds[p]:bounds[p+1]] as written by rank p."""
+    if not dist.is_initialized():
+        return
     world = dist.get_world_size(group)
     if world == 1:
         return
