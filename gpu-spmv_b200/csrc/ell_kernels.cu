@@ -131,6 +131,247 @@ __global__ void zero_rows_kernel(int rows, float* __restrict__ y) {
     if (i < rows) y[i] = 0.0f;
 }
 
+// ---------------------------------------------------------------------------
+// TMA-staged variant.  A CTA owns a window of RPT*256 consecutive rows.  One
+// elected thread issues, for every slice k of the pass, one 1-D bulk copy
+// (cp.async.bulk, SASS UBLKCP) of the window's values and one of its
+// col_indices into shared memory and arms a single mbarrier with the total
+// byte count: the whole window (2 * KS * rows * 4 bytes, 40 KB for the
+// Laplacian) is in flight at once with no register staging and without
+// passing through L1.  Row owners then read their slots from shared memory
+// (stride-1 across a warp: conflict-free), gather x through the read-only
+// path (a warp's rows are adjacent, so a stencil gather touches one or two
+// lines) and accumulate in slice order with separately rounded multiply/add,
+// exactly like ell_slice_kernel.  Thread t owns rows t, t+256, ...
+// Needs rows % 4 == 0 and 16-byte aligned arrays (checked by the launcher).
+template <int RPT>
+__global__ void __launch_bounds__(kEllThreads)
+ell_tma_kernel(int rows, int width, int slices_per_pass, const int* __restrict__ col_indices,
+               const float* __restrict__ values, const float* __restrict__ x, float* __restrict__ y,
+               unsigned long long* __restrict__ nnz_counter) {
+    constexpr int kWindow = RPT * kEllThreads;
+    extern __shared__ __align__(16) unsigned char ell_smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ell_smem);
+    float* s_val = reinterpret_cast<float*>(ell_smem + 16);                       // [slices_per_pass][kWindow]
+    int* s_col = reinterpret_cast<int*>(ell_smem + 16) + slices_per_pass * kWindow;  // [slices_per_pass][kWindow]
+
+    const int tid = threadIdx.x;
+    const long long r0 = static_cast<long long>(blockIdx.x) * kWindow;
+    const int nr = static_cast<int>(min(static_cast<long long>(kWindow), rows - r0));  // multiple of 4
+    const size_t stride = static_cast<size_t>(rows);
+
+    if (tid == 0) {
+        dev::mbar_init(bar, 1);
+        dev::mbar_fence_init();
+    }
+    __syncthreads();
+
+    float acc[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) acc[i] = 0.0f;
+    unsigned live = 0;
+    uint32_t parity = 0;
+
+    for (int k0 = 0; k0 < width; k0 += slices_per_pass) {
+        const int ks = min(slices_per_pass, width - k0);
+        if (tid == 0) {
+            const uint32_t slice_bytes = static_cast<uint32_t>(nr) * sizeof(float);
+            dev::mbar_arrive_expect_tx(bar, 2u * ks * slice_bytes);
+            for (int k = 0; k < ks; ++k) {
+                const size_t off = (k0 + k) * stride + static_cast<size_t>(r0);
+                dev::tma_bulk_g2s(s_val + k * kWindow, values + off, slice_bytes, bar);
+                dev::tma_bulk_g2s(s_col + k * kWindow, col_indices + off, slice_bytes, bar);
+            }
+        }
+        dev::mbar_wait(bar, parity);
+        parity ^= 1u;
+
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int r = tid + i * kEllThreads;
+            if (r < nr) {
+                float a = acc[i];
+#pragma unroll 5
+                for (int k = 0; k < ks; ++k) {
+                    const int c = s_col[k * kWindow + r];
+                    if (c >= 0) {  // padding slots are skipped, not multiplied
+                        a = __fadd_rn(a, __fmul_rn(s_val[k * kWindow + r], dev::ld_x(x + c)));
+                        ++live;
+                    }
+                }
+                acc[i] = a;
+            }
+        }
+        if (k0 + slices_per_pass < width) {
+            __syncthreads();  // every row owner is done with this pass before the buffers are refilled
+            if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = tid + i * kEllThreads;
+        if (r < nr) y[r0 + r] = acc[i];
+    }
+    if (nnz_counter != nullptr) {
+        live = dev::warp_sum(live);
+        if ((tid & 31) == 0 && live) atomicAdd(nnz_counter, static_cast<unsigned long long>(live));
+    }
+}
+
+constexpr int kEllMaxSlicesPerPass = 5;
+
+template <int RPT>
+cudaError_t launch_tma(int rows, int width, const int* ci, const float* va, const float* x, float* y,
+                       unsigned long long* counter, cudaStream_t stream) {
+    constexpr int kWindow = RPT * kEllThreads;
+    const int slices = width < kEllMaxSlicesPerPass ? width : kEllMaxSlicesPerPass;
+    const size_t smem = 16 + static_cast<size_t>(slices) * kWindow * 8;
+    cudaError_t e = cudaFuncSetAttribute(ell_tma_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(16 + kEllMaxSlicesPerPass * kWindow * 8));
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = static_cast<unsigned>((static_cast<long long>(rows) + kWindow - 1) / kWindow);
+    ell_tma_kernel<RPT><<<blocks, kEllThreads, smem, stream>>>(rows, width, slices, ci, va, x, y, counter);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Persistent, multi-stage form of the TMA-staged kernel (width <= 8): the grid
+// is a small multiple of the SM count, CTA b walks windows b, b + grid, ...
+// through a ring of `stages` shared-memory buffers, each guarded by its own
+// mbarrier.  While the row owners consume window i, the bulk copies of windows
+// i+1 .. i+stages-1 are already in flight, so an SM always has
+// ctas_per_sm * (stages-1) * width * 8 * kWindow bytes outstanding and never
+// drains at CTA boundaries.
+template <int RPT>
+__global__ void __launch_bounds__(kEllThreads)
+ell_tma_pipe_kernel(int rows, int width, int stages, const int* __restrict__ col_indices,
+                    const float* __restrict__ values, const float* __restrict__ x, float* __restrict__ y,
+                    unsigned long long* __restrict__ nnz_counter) {
+    constexpr int kWindow = RPT * kEllThreads;
+    extern __shared__ __align__(16) unsigned char ell_smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ell_smem);              // [stages] (<= 16)
+    unsigned char* buffers = ell_smem + 128;
+    const size_t stage_bytes = static_cast<size_t>(width) * kWindow * 8;  // values then col_indices
+
+    const int tid = threadIdx.x;
+    const size_t stride = static_cast<size_t>(rows);
+    const int num_windows = static_cast<int>((static_cast<long long>(rows) + kWindow - 1) / kWindow);
+
+    auto issue = [&](int window, int stage) {  // thread 0 only
+        const long long r0 = static_cast<long long>(window) * kWindow;
+        const int nr = static_cast<int>(min(static_cast<long long>(kWindow), rows - r0));
+        const uint32_t slice_bytes = static_cast<uint32_t>(nr) * sizeof(float);
+        float* s_val = reinterpret_cast<float*>(buffers + stage * stage_bytes);
+        int* s_col = reinterpret_cast<int*>(s_val + width * kWindow);
+        dev::mbar_arrive_expect_tx(bars + stage, 2u * width * slice_bytes);
+        for (int k = 0; k < width; ++k) {
+            const size_t off = k * stride + static_cast<size_t>(r0);
+            dev::tma_bulk_g2s(s_val + k * kWindow, values + off, slice_bytes, bars + stage);
+            dev::tma_bulk_g2s(s_col + k * kWindow, col_indices + off, slice_bytes, bars + stage);
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) dev::mbar_init(bars + s, 1);
+        dev::mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            const int w = blockIdx.x + s * gridDim.x;
+            if (w < num_windows) issue(w, s);
+        }
+    }
+
+    unsigned live = 0;
+    int it = 0;
+    for (int w = blockIdx.x; w < num_windows; w += gridDim.x, ++it) {
+        const int stage = it % stages;
+        const uint32_t parity = (it / stages) & 1u;
+        const long long r0 = static_cast<long long>(w) * kWindow;
+        const int nr = static_cast<int>(min(static_cast<long long>(kWindow), rows - r0));
+        const float* s_val = reinterpret_cast<const float*>(buffers + stage * stage_bytes);
+        const int* s_col = reinterpret_cast<const int*>(s_val + width * kWindow);
+        dev::mbar_wait(bars + stage, parity);
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int r = tid + i * kEllThreads;
+            if (r < nr) {
+                float a = 0.0f;
+#pragma unroll 5
+                for (int k = 0; k < width; ++k) {
+                    const int c = s_col[k * kWindow + r];
+                    if (c >= 0) {
+                        a = __fadd_rn(a, __fmul_rn(s_val[k * kWindow + r], dev::ld_x(x + c)));
+                        ++live;
+                    }
+                }
+                y[r0 + r] = a;
+            }
+        }
+        __syncthreads();  // the stage is free again
+        if (tid == 0) {
+            const int next = w + stages * gridDim.x;
+            if (next < num_windows) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(next, stage);
+            }
+        }
+    }
+    if (nnz_counter != nullptr) {
+        live = dev::warp_sum(live);
+        if ((tid & 31) == 0 && live) atomicAdd(nnz_counter, static_cast<unsigned long long>(live));
+    }
+}
+
+int env_int(const char* name, int fallback) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : fallback;
+}
+
+template <int RPT>
+cudaError_t launch_tma_pipe(int rows, int width, const int* ci, const float* va, const float* x, float* y,
+                            unsigned long long* counter, cudaStream_t stream) {
+    constexpr int kWindow = RPT * kEllThreads;
+    static const int env_stages = env_int("SPMV_B200_ELL_STAGES", 0);
+    static const int env_ctas = env_int("SPMV_B200_ELL_CTAS_PER_SM", 0);
+    const size_t stage_bytes = static_cast<size_t>(width) * kWindow * 8;
+    // Measured on B200 (profiles/r1_ell_tuning.md): the consumer side (x gathers) needs every
+    // thread slot of the SM, the ring only needs two stages -> 2 stages, as many CTAs as fit (<= 8).
+    int stages = env_stages > 0 ? env_stages : 2;
+    if (stages > 16) stages = 16;
+    if (stages < 2) stages = 2;
+    const size_t smem = 128 + stages * stage_bytes;
+    int fit = static_cast<int>((220 * 1024) / (smem + 1024));
+    if (fit > 2048 / kEllThreads) fit = 2048 / kEllThreads;
+    if (fit < 1) fit = 1;
+    const int ctas_per_sm = env_ctas > 0 ? env_ctas : fit;
+    cudaError_t e = cudaFuncSetAttribute(ell_tma_pipe_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    int sms = 148, dev_id = 0;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    const int num_windows = static_cast<int>((static_cast<long long>(rows) + kWindow - 1) / kWindow);
+    int blocks = sms * ctas_per_sm;
+    if (blocks > num_windows) blocks = num_windows;
+    ell_tma_pipe_kernel<RPT><<<blocks, kEllThreads, smem, stream>>>(rows, width, stages, ci, va, x, y, counter);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+// 0 = automatic; 1 = register-staged kernel; 2 / 3 = TMA-staged with 4 / 2 rows per thread;
+// 4 / 5 / 6 = persistent TMA pipeline with 4 / 2 / 1 rows per thread.
+// (SPMV_B200_ELL_VARIANT exists for A/B timing on the device; see profiles/.)
+int ell_variant_override() {
+    static const int v = [] {
+        const char* s = getenv("SPMV_B200_ELL_VARIANT");
+        return s ? atoi(s) : 0;
+    }();
+    return v;
+}
+
 }  // namespace
 
 cudaError_t launch_ell(int rows, int width, const int* col_indices, const float* values,
@@ -141,8 +382,17 @@ cudaError_t launch_ell(int rows, int width, const int* col_indices, const float*
         count_launches(1);
         return cudaGetLastError();
     }
-    if (rows % 4 == 0 && all_aligned(col_indices, values, y, 16))
-        return launch_rpt<4>(rows, width, col_indices, values, x, y, nnz_counter, stream);
+    if (rows % 4 == 0 && all_aligned(col_indices, values, y, 16)) {
+        const int variant = ell_variant_override();
+        if (variant == 1) return launch_rpt<4>(rows, width, col_indices, values, x, y, nnz_counter, stream);
+        if (variant == 2) return launch_tma<4>(rows, width, col_indices, values, x, y, nnz_counter, stream);
+        if (width <= 8) {
+            if (variant == 4) return launch_tma_pipe<4>(rows, width, col_indices, values, x, y, nnz_counter, stream);
+            if (variant == 5) return launch_tma_pipe<2>(rows, width, col_indices, values, x, y, nnz_counter, stream);
+            if (variant != 3) return launch_tma_pipe<1>(rows, width, col_indices, values, x, y, nnz_counter, stream);
+        }
+        return launch_tma<2>(rows, width, col_indices, values, x, y, nnz_counter, stream);
+    }
     if (rows % 2 == 0 && all_aligned(col_indices, values, y, 8))
         return launch_rpt<2>(rows, width, col_indices, values, x, y, nnz_counter, stream);
     return launch_rpt<1>(rows, width, col_indices, values, x, y, nnz_counter, stream);
