@@ -218,6 +218,232 @@ cudaError_t launch_stream_lpr(const CsrView& A, const float* x, float* y, cudaSt
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// csr_pipe_kernel<LPR, U>: the persistent, TMA-staged form of the row-owner
+// kernel (the default when the arrays are 16-byte aligned).
+//
+// The grid is a small multiple of the SM count; CTA b walks row windows b,
+// b + grid, ... through a ring of `stages` shared-memory buffers, each guarded
+// by an mbarrier.  For a window the elected thread issues three 1-D bulk
+// copies (cp.async.bulk, SASS UBLKCP): the window's row_ptrs, and the 16-byte
+// aligned span of values and of col_indices that covers the window's
+// contiguous non-zero range.  Nothing is staged through registers or L1 and a
+// window's bytes are all in flight at once, while the previous window is
+// being consumed.  Row owners (LPR lanes per row) then read value / column
+// pairs from shared memory, gather x through the read-only path and
+// accumulate; LPR == 1 keeps the sequential separately-rounded order, so the
+// result stays bit-identical to spmv_cpu_csr.
+//
+// Corner cases are handled per element rather than per launch: non-zeros
+// outside the staged span (a window larger than the stage capacity, or the
+// last <4 non-zeros of the matrix, which a 16-byte granular copy cannot
+// reach without reading past the array) are fetched from global memory, and
+// so are the row_ptrs of the last window (its copy would over-read).
+struct PipeStageHeader {
+    int base;         // non-zero index held by slot 0 of the stage
+    int staged_end;   // non-zeros [base, staged_end) are in shared memory
+    int rp_staged;    // row_ptrs of the window are in shared memory
+    int pad;
+};
+
+template <int LPR, int U>
+__global__ void __launch_bounds__(kThreads)
+csr_pipe_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* __restrict__ col_indices,
+                const float* __restrict__ values, const float* __restrict__ x, float* __restrict__ y,
+                int window_rows, int rows_per_group, int cap, int stages) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [stages] (<= 16)
+    unsigned char* ring = smem_raw + 128;
+    const size_t stage_bytes = sizeof(PipeStageHeader) + static_cast<size_t>(window_rows + 4) * 4 +
+                               static_cast<size_t>(cap) * 8;
+    constexpr int kGroups = kThreads / LPR;
+    // U = gathers per row and batch (template parameter: 4, 6 or 8)
+    const int tid = threadIdx.x;
+    const int group = tid / LPR;
+    const int lane = tid % LPR;
+    const int num_windows = (rows + window_rows - 1) / window_rows;
+
+    auto stage_header = [&](int s) { return reinterpret_cast<PipeStageHeader*>(ring + s * stage_bytes); };
+    auto stage_rp = [&](int s) { return reinterpret_cast<int*>(ring + s * stage_bytes + sizeof(PipeStageHeader)); };
+    auto stage_val = [&](int s) { return reinterpret_cast<float*>(stage_rp(s) + window_rows + 4); };
+    auto stage_col = [&](int s) { return reinterpret_cast<int*>(stage_val(s) + cap); };
+
+    // thread 0 only; n0 / n1 = first / one-past-last non-zero of the window
+    auto issue = [&](int w, int s, int n0, int n1) {
+        const int r0 = w * window_rows;
+        const int base = n0 & ~3;
+        int end = min((n1 + 3) & ~3, nnz & ~3);
+        end = min(end, base + cap);
+        end = max(end, base);
+        const bool rp_ok = r0 + window_rows + 4 <= rows + 1;
+        PipeStageHeader* h = stage_header(s);
+        h->base = base;
+        h->staged_end = end;
+        h->rp_staged = rp_ok ? 1 : 0;
+        const uint32_t nz_bytes = static_cast<uint32_t>(end - base) * 4u;
+        const uint32_t rp_bytes = rp_ok ? static_cast<uint32_t>(window_rows + 4) * 4u : 0u;
+        dev::mbar_arrive_expect_tx(bars + s, 2u * nz_bytes + rp_bytes);
+        if (rp_bytes) dev::tma_bulk_g2s(stage_rp(s), row_ptrs + r0, rp_bytes, bars + s);
+        if (nz_bytes) {
+            dev::tma_bulk_g2s(stage_val(s), values + base, nz_bytes, bars + s);
+            dev::tma_bulk_g2s(stage_col(s), col_indices + base, nz_bytes, bars + s);
+        }
+    };
+    auto window_bounds = [&](int w, int& n0, int& n1) {
+        const int r0 = w * window_rows;
+        n0 = __ldg(row_ptrs + r0);
+        n1 = __ldg(row_ptrs + min(r0 + window_rows, rows));
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) dev::mbar_init(bars + s, 1);
+        dev::mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            const int w = blockIdx.x + s * gridDim.x;
+            if (w < num_windows) {
+                int n0, n1;
+                window_bounds(w, n0, n1);
+                issue(w, s, n0, n1);
+            }
+        }
+    }
+
+    int it = 0;
+    for (int w = blockIdx.x; w < num_windows; w += gridDim.x, ++it) {
+        const int s = it % stages;
+        const uint32_t parity = (it / stages) & 1u;
+        const int next = w + stages * gridDim.x;
+        int next_n0 = 0, next_n1 = 0;
+        if (tid == 0 && next < num_windows) window_bounds(next, next_n0, next_n1);  // latency hidden by the consume phase
+
+        dev::mbar_wait(bars + s, parity);
+        const PipeStageHeader h = *stage_header(s);
+        const int* s_rp = stage_rp(s);
+        const float* s_val = stage_val(s);
+        const int* s_col = stage_col(s);
+        const int r0 = w * window_rows;
+        const int nr = min(window_rows, rows - r0);
+
+        // U elements of a row are gathered per batch, so up to U independent x gathers are in
+        // flight per thread (one gather latency for rows up to U*LPR long).
+        for (int i = 0; i < rows_per_group; ++i) {
+            const int r = group + i * kGroups;
+            float acc = 0.0f;
+            if (r < nr) {
+                const int a = h.rp_staged ? s_rp[r] : __ldg(row_ptrs + r0 + r);
+                const int b = h.rp_staged ? s_rp[r + 1] : __ldg(row_ptrs + r0 + r + 1);
+                for (int j = a + lane; j < b; j += U * LPR) {
+                    float v[U], xv[U];
+                    int c[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int ju = j + u * LPR;
+                        if (ju < b) {
+                            if (ju < h.staged_end) {
+                                v[u] = s_val[ju - h.base];
+                                c[u] = s_col[ju - h.base];
+                            } else {
+                                v[u] = dev::ld_stream_f(values + ju);
+                                c[u] = dev::ld_stream_i(col_indices + ju);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (j + u * LPR < b) xv[u] = dev::ld_x(x + c[u]);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (j + u * LPR < b) acc = __fadd_rn(acc, __fmul_rn(v[u], xv[u]));
+                }
+            }
+#pragma unroll
+            for (int d = LPR / 2; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, LPR);
+            if (lane == 0 && r < nr) y[r0 + r] = acc;
+        }
+        __syncthreads();  // stage s is free again
+        if (tid == 0 && next < num_windows) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(next, s, next_n0, next_n1);
+        }
+    }
+}
+
+int stream_env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : fallback;
+}
+
+template <int LPR, int U>
+cudaError_t launch_pipe_lpr_u(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
+    constexpr int groups = kThreads / LPR;
+    const double avg = static_cast<double>(A.nnz) / A.rows;
+    // window = groups * rows_per_group rows holding about 1.5 K non-zeros
+    int rpg = static_cast<int>(1536.0 / (avg * groups) + 0.5);
+    static const int env_rpg = stream_env_int("SPMV_B200_CSR_RPG", 0);
+    if (env_rpg > 0) rpg = env_rpg;
+    rpg = rpg < 1 ? 1 : (rpg > 8 ? 8 : rpg);
+    const int window = groups * rpg;
+    int cap = static_cast<int>(1.125 * avg * window) + 32;  // windows that exceed it fetch the excess from global
+    cap = (cap + 127) / 128 * 128;
+    static const int env_stages = stream_env_int("SPMV_B200_CSR_STAGES", 0);
+    static const int env_ctas = stream_env_int("SPMV_B200_CSR_CTAS_PER_SM", 0);
+    const int stages = env_stages > 1 ? (env_stages > 16 ? 16 : env_stages) : 2;
+    const size_t stage_bytes = sizeof(PipeStageHeader) + static_cast<size_t>(window + 4) * 4 + static_cast<size_t>(cap) * 8;
+    const size_t smem = 128 + stages * stage_bytes;
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // caller falls back
+    cudaError_t e = cudaFuncSetAttribute(csr_pipe_kernel<LPR, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    // A persistent grid must not exceed what is co-resident (registers AND shared memory),
+    // otherwise the surplus CTAs only start when the first wave has finished.
+    int fit = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, csr_pipe_kernel<LPR, U>, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (fit < 1) return cudaErrorInvalidConfiguration;
+    const int ctas_per_sm = (env_ctas > 0 && env_ctas < fit) ? env_ctas : fit;
+    int sms = 148, dev_id = 0;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    const int num_windows = (A.rows + window - 1) / window;
+    int blocks = sms * ctas_per_sm;
+    if (blocks > num_windows) blocks = num_windows;
+    csr_pipe_kernel<LPR, U><<<blocks, kThreads, smem, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values, x, y,
+                                                             window, rpg, cap, stages);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+// gathers per batch: enough to cover an average row of the group's lanes in one batch
+template <int LPR>
+cudaError_t launch_pipe_lpr(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
+    static const int env_u = stream_env_int("SPMV_B200_CSR_U", 0);
+    const double per_lane = static_cast<double>(A.nnz) / A.rows / LPR;
+    int u = per_lane <= 4.0 ? 4 : (per_lane <= 6.0 ? 6 : 8);
+    if (env_u > 0) u = env_u;
+    if (u <= 4) return launch_pipe_lpr_u<LPR, 4>(A, x, y, stream);
+    if (u <= 6) return launch_pipe_lpr_u<LPR, 6>(A, x, y, stream);
+    return launch_pipe_lpr_u<LPR, 8>(A, x, y, stream);
+}
+
+bool pipe_eligible(const CsrView& A) {
+    static const int disable = stream_env_int("SPMV_B200_CSR_NO_PIPE", 0);
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(A.values) | reinterpret_cast<uintptr_t>(A.col_indices) |
+                           reinterpret_cast<uintptr_t>(A.row_ptrs);
+    return !disable && (bits & 15u) == 0;
+}
+
+template <int LPR>
+cudaError_t launch_best_lpr(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
+    if (pipe_eligible(A)) {
+        const cudaError_t e = launch_pipe_lpr<LPR>(A, x, y, stream);
+        if (e != cudaErrorInvalidConfiguration) return e;
+    }
+    return launch_stream_lpr<LPR>(A, x, y, stream);
+}
+
 }  // namespace
 
 cudaError_t launch_csr_stream(const CsrView& A, const float* x, float* y, int lanes_per_row,
@@ -227,6 +453,13 @@ cudaError_t launch_csr_stream(const CsrView& A, const float* x, float* y, int la
         zero_rows_kernel<<<(A.rows + 255) / 256, 256, 0, stream>>>(A.rows, y);
         count_launches(1);
         return cudaGetLastError();
+    }
+    switch (lanes_per_row) {
+        case 1:  return launch_best_lpr<1>(A, x, y, stream);
+        case 2:  return launch_best_lpr<2>(A, x, y, stream);
+        case 4:  return launch_best_lpr<4>(A, x, y, stream);
+        case 8:  return launch_best_lpr<8>(A, x, y, stream);
+        case 16: return launch_best_lpr<16>(A, x, y, stream);
     }
     switch (lanes_per_row) {
         case 1:  return launch_stream_lpr<1>(A, x, y, stream);

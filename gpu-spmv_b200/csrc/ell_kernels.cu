@@ -343,13 +343,15 @@ cudaError_t launch_tma_pipe(int rows, int width, const int* ci, const float* va,
     if (stages > 16) stages = 16;
     if (stages < 2) stages = 2;
     const size_t smem = 128 + stages * stage_bytes;
-    int fit = static_cast<int>((220 * 1024) / (smem + 1024));
-    if (fit > 2048 / kEllThreads) fit = 2048 / kEllThreads;
-    if (fit < 1) fit = 1;
-    const int ctas_per_sm = env_ctas > 0 ? env_ctas : fit;
     cudaError_t e = cudaFuncSetAttribute(ell_tma_pipe_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
+    // a persistent grid must not exceed what is co-resident (registers and shared memory)
+    int fit = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, ell_tma_pipe_kernel<RPT>, kEllThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (fit < 1) fit = 1;
+    const int ctas_per_sm = (env_ctas > 0 && env_ctas < fit) ? env_ctas : fit;
     int sms = 148, dev_id = 0;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
