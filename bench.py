@@ -393,10 +393,9 @@ def run_product_arm(args):
         torch.cuda.empty_cache()
 
     # ---- config 4 / 5: R-MAT SpMV (merge-path) and PageRank, row-sharded over the ranks -----------
-    log("R-MAT build + SpMV")
-    if not args.quick:
-        scale = args.rmat_scale
-        n, bounds, srp, sci, sva, n_edges = build_rmat_shard(torch, gen, scale, 16, 44, rank, world, dev)
+    def rmat_section(scale, seed, do_vector, do_pagerank):
+        log(f"R-MAT scale {scale}: build")
+        n, bounds, srp, sci, sva, n_edges = build_rmat_shard(torch, gen, scale, 16, seed, rank, world, dev)
         torch.cuda.synchronize()
         shard = D.CudaShard(n, bounds[rank], srp, sci, sva, stream=s_ptr)
         xg = torch.full((n,), 1.0 / n, dtype=torch.float32, device=dev)
@@ -406,49 +405,63 @@ def run_product_arm(args):
         tot4 = torch.tensor([float(b4)], dtype=torch.float64, device=dev)
         if dist_on:
             dist.all_reduce(tot4)
-        for kernel, name in ((sp.MERGE_PATH, "csr_merge"), (sp.VECTOR_CSR, "csr_vector")):
+        kernels = [(sp.MERGE_PATH, "csr_merge")] + ([(sp.VECTOR_CSR, "csr_vector")] if do_vector else [])
+        for kernel, name in kernels:
+            log(f"R-MAT scale {scale}: {name}")
             r = bench_kernel(torch, sp, stream, lambda: shard.spmv(xg, yg, kernel), 0, max(5, args.steps // 2), 3, dist_on)
             gbs = float(tot4.item()) / (r["ms_per_step"] * 1e-3) / 1e9
             extra[f"rmat{scale}_{name}"] = {"gbs": gbs, "ms": r["ms_per_step"], "frac_of_measured_peak": gbs / world / peak,
                                             "frac_of_8000": gbs / world / 8000.0, "bytes_all_ranks": float(tot4.item()),
-                                            "nnz": n_edges, "rows": n}
-        # PageRank: fixed number of iterations of the sharded loop, device-timed, max over ranks
-        log("PageRank")
-        shard.damping = 0.85
-        with torch.cuda.stream(stream):
-            shard.setup_dangling()
-            r_a = torch.empty(n, dtype=torch.float32, device=dev)
-            r_b = torch.empty_like(r_a)
-            partial = torch.zeros(3, dtype=torch.float64, device=dev)
-            shard.init_vector(r_a)
-            D.pagerank_loop(shard, r_a, r_b, partial, bounds, 0.85, 0.0, 0, fixed_iterations=3)  # warm-up
-            shard.init_vector(r_a)
+                                            "nnz": n_edges, "rows": n, "scaling": "strong (one graph, row shards)"}
+        if do_pagerank:
+            # fixed number of iterations of the sharded loop (stop rule evaluated every iteration,
+            # one iteration late), wall clock around the loop after a device sync, max over ranks
+            log(f"R-MAT scale {scale}: PageRank")
+            shard.damping = 0.85
+            with torch.cuda.stream(stream):
+                shard.setup_dangling()
+                r_a = torch.empty(n, dtype=torch.float32, device=dev)
+                r_b = torch.empty_like(r_a)
+                partial = torch.zeros(3, dtype=torch.float64, device=dev)
+                shard.init_vector(r_a)
+                D.pagerank_loop(shard, r_a, r_b, partial, bounds, 0.85, 0.0, 0, fixed_iterations=3)  # warm-up
+                shard.init_vector(r_a)
+                if dist_on:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                iters = args.pr_iters
+                t0 = time.perf_counter()
+                fin, done, residual, conv, l1 = D.pagerank_loop(shard, r_a, r_b, partial, bounds, 0.85, 0.0, 0,
+                                                                fixed_iterations=iters)
+                torch.cuda.synchronize()
+                sec = time.perf_counter() - t0
             if dist_on:
-                dist.barrier()
-            torch.cuda.synchronize()
-            iters = args.pr_iters
-            t0 = time.perf_counter()
-            fin, done, residual, conv, l1 = D.pagerank_loop(shard, r_a, r_b, partial, bounds, 0.85, 0.0, 0,
-                                                            fixed_iterations=iters)
-            torch.cuda.synchronize()
-            sec = time.perf_counter() - t0
-        if dist_on:
-            t = torch.tensor([sec], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            sec = float(t.item())
-        it_bytes = float(tot4.item())
-        extra["pagerank"] = {"iters_per_s": iters / sec, "ms_per_iter": sec / iters * 1e3, "graph": f"R-MAT scale {scale} x16",
-                             "n": n, "nnz": n_edges, "iterations_timed": iters, "l2_residual_after": residual,
-                             "effective_gbs": it_bytes / (sec / iters) / 1e9, "scaling": "strong",
-                             "frac_of_measured_peak": it_bytes / (sec / iters) / 1e9 / world / peak,
-                             "collectives": "all-gather of rank slices + all-reduce of 3 f64 (NCCL)" if dist_on else "none (1 GPU)",
-                             "includes": "per-iteration host read of the residual (stop rule), excluded: setup + final normalisation"}
+                t = torch.tensor([sec], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sec = float(t.item())
+            it_bytes = float(tot4.item())
+            extra["pagerank"] = {"iters_per_s": iters / sec, "ms_per_iter": sec / iters * 1e3,
+                                 "graph": f"R-MAT scale {scale} x16, d=0.85", "n": n, "nnz": n_edges,
+                                 "iterations_timed": iters, "l2_residual_after": residual,
+                                 "effective_gbs": it_bytes / (sec / iters) / 1e9, "scaling": "strong",
+                                 "frac_of_measured_peak": it_bytes / (sec / iters) / 1e9 / world / peak,
+                                 "collectives": ("all-gather of rank slices + all-reduce of 3 f64 (NCCL)" if dist_on
+                                                 else "none (1 GPU)"),
+                                 "includes": "fused step + collectives + lagged host read of the residual every iteration; "
+                                             "excluded: setup + final normalisation"}
         shard.close()
+        del shard, srp, sci, sva, xg, yg
+        torch.cuda.empty_cache()
+
+    if not args.quick:
+        rmat_section(args.rmat_scale, 44, do_vector=(world == 1), do_pagerank=(args.pr_scale == args.rmat_scale))
+        if args.pr_scale != args.rmat_scale:
+            rmat_section(args.pr_scale, 45, do_vector=False, do_pagerank=True)
 
     if rank == 0:
         roofline = {"bound": "hbm", "achieved": launch_gbs, "peak": peak, "unit": "GB/s", "frac": launch_gbs / peak,
                     "peak_source": peak_src, "frac_of_8000_nominal": launch_gbs / 8000.0,
-                    "kernel": "ell_slice_kernel<4>", "algorithmic_bytes_per_launch": ell_bytes,
+                    "kernel": "ell_tma_pipe_kernel<1>", "algorithmic_bytes_per_launch": ell_bytes,
                     "traffic": args.ncu_traffic}
         line = {
             "metric": "spmv_effective_hbm_gbs", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -474,7 +487,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--quick", action="store_true", help="headline + e2e + cpu baseline only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--rmat-scale", type=int, default=24)
+    ap.add_argument("--rmat-scale", type=int, default=24, help="BASELINE config 4: R-MAT SpMV")
+    ap.add_argument("--pr-scale", type=int, default=26, help="BASELINE config 5: PageRank graph")
     ap.add_argument("--c3-rows", type=int, default=50_000_000)
     ap.add_argument("--pr-iters", type=int, default=20)
     ap.add_argument("--ncu-traffic", type=float, default=None,

@@ -174,9 +174,11 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
                   const int* __restrict__ col_indices, const float* __restrict__ values,
                   const float* __restrict__ x, const int2* __restrict__ coords,
                   int* __restrict__ carry_row, float* __restrict__ carry_val, Row row_op,
-                  double* __restrict__ partials) {
-    __shared__ int s_end[kTile + 1];            // global END offset of tile-local row i
-    __shared__ __align__(16) float s_prod[kTile + 4];
+                  double* __restrict__ partials, int use_tma) {
+    __shared__ __align__(16) int s_end_raw[kTile + 8];  // global END offset of tile-local row i (+ alignment shift)
+    __shared__ __align__(16) float s_prod[kTile + 4];   // values, then products in place
+    extern __shared__ __align__(16) int s_col[];        // [kTile + 4], allocated for the TMA path only
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ float s_warp_val[kT / 32];
     __shared__ int s_warp_flag[kT / 32];
     __shared__ double s_sums[kT / 32][3];
@@ -193,30 +195,72 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
 
     row_op.prepare();
 
-    // ---- stage row ends (tile_rows + 1 entries; the last one bounds the open row)
-    for (int i = tid; i <= tile_rows; i += kT)
-        s_end[i] = (row_s + i < rows) ? dev::ld_stream_i(row_ptrs + row_s + 1 + i) : INT_MAX;
-
-    // ---- stage products of non-zeros [nz_s, nz_e) at slot (j - base) ----------
     const int base = nz_s & ~3;
     const bool vec_ok = dev::aligned16(values) && dev::aligned16(col_indices);  // any device pointer is legal
+
+    // ---- TMA path: three 1-D bulk copies (row ends, values, col_indices of the tile) onto one
+    // mbarrier; the stream bypasses registers and L1, which on scale-free inputs is the unit that
+    // saturates (one L1 wavefront per gathered x element).  Needs 16-byte aligned arrays and spans
+    // that stay inside them, i.e. every tile except the last one or two.
+    const int end_first = (row_s + 1) & ~3;                         // aligned start of the row-end span
+    const int end_count = ((row_s + 1 + tile_rows + 1 + 3) & ~3) - end_first;
+    const int nz_end4 = (nz_e + 3) & ~3;
+    auto gather = [&](int c) { return dev::ld_x(x + c); };  // L1-allocating: hub columns hit (no_allocate measured slower)
+    const bool tma_ok = use_tma && vec_ok && dev::aligned16(row_ptrs) && (c1.x < rows) &&
+                        (end_first + end_count <= rows + 1) && (nz_end4 <= (nnz & ~3)) && (nz_e > nz_s);
+    const int* s_end = s_end_raw + (tma_ok ? (row_s + 1 - end_first) : 0);
+    if (tma_ok) {
+        if (tid == 0) {
+            dev::mbar_init(&s_bar, 1);
+            dev::mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t nz_bytes = static_cast<uint32_t>(nz_end4 - base) * 4u;
+            const uint32_t end_bytes = static_cast<uint32_t>(end_count) * 4u;
+            dev::mbar_arrive_expect_tx(&s_bar, 2u * nz_bytes + end_bytes);
+            dev::tma_bulk_g2s(s_end_raw, row_ptrs + end_first, end_bytes, &s_bar);
+            dev::tma_bulk_g2s(s_prod, values + base, nz_bytes, &s_bar);
+            dev::tma_bulk_g2s(s_col, col_indices + base, nz_bytes, &s_bar);
+        }
+        dev::mbar_wait(&s_bar, 0);
+        // products in place: all gathers of a thread are issued before the first multiply
+        constexpr int kPer = (kTile + kT - 1) / kT;
+        float xv[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int j = nz_s + tid + u * kT;
+            if (j < nz_e) xv[u] = gather(s_col[j - base]);
+        }
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int j = nz_s + tid + u * kT;
+            if (j < nz_e) s_prod[j - base] *= xv[u];
+        }
+    } else {
+    // ---- stage row ends (tile_rows + 1 entries; the last one bounds the open row)
+    for (int i = tid; i <= tile_rows; i += kT)
+        s_end_raw[i] = (row_s + i < rows) ? dev::ld_stream_i(row_ptrs + row_s + 1 + i) : INT_MAX;
+
+    // ---- stage products of non-zeros [nz_s, nz_e) at slot (j - base) ----------
     for (int j = base + 4 * tid; j < nz_e; j += 4 * kT) {
         float p0, p1, p2, p3;
         if (vec_ok && j >= nz_s && j + 4 <= nz_e) {
             const float4 v = dev::ld_stream_f4(values + j);
             const int4 c = dev::ld_stream_i4(col_indices + j);
-            p0 = v.x * dev::ld_x(x + c.x);
-            p1 = v.y * dev::ld_x(x + c.y);
-            p2 = v.z * dev::ld_x(x + c.z);
-            p3 = v.w * dev::ld_x(x + c.w);
+            p0 = v.x * gather(c.x);
+            p1 = v.y * gather(c.y);
+            p2 = v.z * gather(c.z);
+            p3 = v.w * gather(c.w);
         } else {
-            p0 = (j + 0 >= nz_s && j + 0 < nz_e) ? values[j + 0] * dev::ld_x(x + col_indices[j + 0]) : 0.0f;
-            p1 = (j + 1 >= nz_s && j + 1 < nz_e) ? values[j + 1] * dev::ld_x(x + col_indices[j + 1]) : 0.0f;
-            p2 = (j + 2 >= nz_s && j + 2 < nz_e) ? values[j + 2] * dev::ld_x(x + col_indices[j + 2]) : 0.0f;
-            p3 = (j + 3 >= nz_s && j + 3 < nz_e) ? values[j + 3] * dev::ld_x(x + col_indices[j + 3]) : 0.0f;
+            p0 = (j + 0 >= nz_s && j + 0 < nz_e) ? values[j + 0] * gather(col_indices[j + 0]) : 0.0f;
+            p1 = (j + 1 >= nz_s && j + 1 < nz_e) ? values[j + 1] * gather(col_indices[j + 1]) : 0.0f;
+            p2 = (j + 2 >= nz_s && j + 2 < nz_e) ? values[j + 2] * gather(col_indices[j + 2]) : 0.0f;
+            p3 = (j + 3 >= nz_s && j + 3 < nz_e) ? values[j + 3] * gather(col_indices[j + 3]) : 0.0f;
         }
         *reinterpret_cast<float4*>(s_prod + (j - base)) = make_float4(p0, p1, p2, p3);
     }
+    }  // register-staged path
     // does the tile's first row own non-zeros in earlier tiles?
     const bool first_row_split = (row_s < rows) && (nz_s > __ldg(row_ptrs + row_s));
     __syncthreads();
@@ -361,13 +405,22 @@ __global__ void zero_rows_kernel(int rows, float* __restrict__ y) {
     if (i < rows) y[i] = 0.0f;
 }
 
+int merge_env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : fallback;
+}
+
 template <class Row>
 cudaError_t run_tiles(const CsrView& A, const float* x, const MergePlan& plan, const Row& row_op,
                       cudaStream_t stream) {
     if (plan.num_tiles <= 0) return cudaSuccess;
-    merge_tile_kernel<Row><<<plan.num_tiles, kT, 0, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values, x,
-                                                              plan.coords, plan.carry_row, plan.carry_val, row_op,
-                                                              plan.partials);
+    static const int use_tma = merge_env_int("SPMV_B200_MERGE_TMA", 0);
+    static const int carveout = merge_env_int("SPMV_B200_MERGE_CARVEOUT", -1);
+    if (carveout >= 0) cudaFuncSetAttribute(merge_tile_kernel<Row>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+    const size_t dyn_smem = use_tma ? (kTile + 4) * sizeof(int) : 0;
+    merge_tile_kernel<Row><<<plan.num_tiles, kT, dyn_smem, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values,
+                                                                     x, plan.coords, plan.carry_row, plan.carry_val,
+                                                                     row_op, plan.partials, use_tma);
     merge_fixup_kernel<Row><<<plan.fixup_blocks, 256, 0, stream>>>(plan.num_tiles, plan.carry_row, plan.carry_val,
                                                                    row_op, plan.partials);
     count_launches(2);

@@ -125,7 +125,7 @@ int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d
               cudaMalloc(&d_bits, sizeof(uint32_t) * words) == cudaSuccess &&
               cudaMalloc(&d_dsum, sizeof(float)) == cudaSuccess &&
               cudaMalloc(&d_partial, 3 * sizeof(double)) == cudaSuccess &&
-              cudaMallocHost(&h_partial, 3 * sizeof(double)) == cudaSuccess;
+              cudaMallocHost(&h_partial, 6 * sizeof(double)) == cudaSuccess;
     auto cleanup = [&]() {
         cudaFree(d_a); cudaFree(d_b); cudaFree(d_colsum); cudaFree(d_bits); cudaFree(d_dsum); cudaFree(d_partial);
         if (h_partial) cudaFreeHost(h_partial);
@@ -144,35 +144,57 @@ int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d
     // r = 1/n and its dangling mass (reference :69-72, :94-99 for iteration 0)
     launch_pr_init(n, d_bits, d_a, d_dsum, plan->tmp, stream);
 
+    // The stop rule is the reference's (L2 norm of the delta < tolerance, every iteration,
+    // :118-127) but it is read one iteration late: the 24-byte sums of iteration i go to pinned
+    // host memory asynchronously and are inspected while iteration i+1 is already queued, so the
+    // device never idles on the host.  If iteration i had converged, its output is the INPUT of
+    // the speculative iteration i+1 (which writes the other buffer), so vector, iteration count
+    // and residual are exactly those of the eager rule.
     float* r_old = d_a;
     float* r_new = d_b;
-    bool from_new = false;
+    const float* fin = r_old;  // what the reference returns when the loop never runs (:135-139)
     int iters = 0;
     float residual = 0.0f;
     double l1 = 0.0;
     bool conv = false;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    struct Pending { int iter; int slot; const float* vec; bool valid; } pending = {0, 0, nullptr, false};
+    auto settle = [&](const Pending& p) -> bool {  // true when that iteration met the tolerance
+        if (cudaEventSynchronize(ev[p.slot]) != cudaSuccess) {
+            cudaGetLastError();
+            rc = static_cast<int>(SpMVError::KERNEL_LAUNCH);
+            return true;
+        }
+        residual = std::sqrt(static_cast<float>(h_partial[3 * p.slot + 0]));  // L2 norm of the delta (:118)
+        l1 = h_partial[3 * p.slot + 1];
+        iters = p.iter;
+        fin = p.vec;
+        return residual < config->tolerance;  // :123-127
+    };
     for (int it = 0; it < config->max_iterations; ++it) {
         rc = pr_step(plan, r_old, r_new, config->damping_factor, d_dsum, d_bits, d_partial, stream);
         if (rc != 0) break;  // the reference also leaves the loop on a failed SpMV (:105-107)
         launch_next_dsum(d_partial, d_dsum, stream);
-        cudaMemcpyAsync(h_partial, d_partial, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
-        if (cudaStreamSynchronize(stream) != cudaSuccess) {
-            cudaGetLastError();
-            rc = static_cast<int>(SpMVError::KERNEL_LAUNCH);
-            break;
+        const int slot = it & 1;
+        cudaMemcpyAsync(h_partial + 3 * slot, d_partial, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
+        cudaEventRecord(ev[slot], stream);
+        if (pending.valid) {
+            const bool done = settle(pending);
+            pending.valid = false;
+            if (done) {
+                conv = rc == 0;
+                break;
+            }
         }
-        residual = std::sqrt(static_cast<float>(h_partial[0]));  // L2 norm of the delta (:118)
-        l1 = h_partial[1];
-        iters = it + 1;
-        if (residual < config->tolerance) {  // :123-127
-            conv = true;
-            from_new = true;
-            break;
-        }
+        pending = {it + 1, slot, r_new, true};
         float* t = r_old; r_old = r_new; r_new = t;  // :130-131
     }
+    if (pending.valid && rc == 0) conv = settle(pending) && rc == 0;
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
     // final vector (:135-139) and normalisation (:142-150)
-    const float* fin = from_new ? r_new : r_old;
     if (normalize) launch_normalize(fin, n, d_ranks, plan->tmp, stream);
     else cudaMemcpyAsync(d_ranks, fin, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream);
     cudaError_t e = cudaStreamSynchronize(stream);

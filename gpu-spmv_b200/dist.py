@@ -92,29 +92,60 @@ def pagerank_loop(step, r_old, r_new, partial, bounds, damping, tolerance, max_i
     step(r_old, r_new, partial) must write this rank's slice of r_new and its
     three partial sums (float64 tensor [3]: sum d^2, sum |d|, next dangling mass)
     and is told the all-reduced dangling mass through step.set_dangling_mass().
-    Returns (final vector, iterations, residual, converged, l1)."""
-    iters, residual, l1, conv, from_new = 0, 0.0, 0.0, False, False
+
+    The stop rule is the reference's (L2 norm of the delta < tolerance, evaluated for EVERY
+    iteration), but it is evaluated one iteration late: the 24-byte sums of iteration i are
+    copied to pinned host memory asynchronously and read while iteration i+1 is already queued,
+    so the device never idles on the host.  If iteration i turns out to have converged, its
+    output -- the INPUT buffer of the speculative iteration i+1, which that iteration does not
+    write -- is returned; iteration count, residual and vector are exactly those of the eager
+    rule.  Returns (final vector, iterations, residual, converged, l1)."""
     limit = fixed_iterations if fixed_iterations > 0 else max_iterations
+    on_gpu = partial.is_cuda
+    host_bufs = [torch.empty(3, dtype=torch.float64, pin_memory=on_gpu) for _ in range(2)]
+    events = [torch.cuda.Event() for _ in range(2)] if on_gpu else [None, None]
+    distributed = dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def read(slot):
+        if on_gpu:
+            events[slot].synchronize()
+        host = host_bufs[slot]
+        res = float(np.sqrt(np.float32(host[0].item())))  # L2 norm of the delta in fp32 (src/pagerank.cu:118)
+        return res, float(host[1].item())
+
+    iters, residual, l1, conv = 0, 0.0, 0.0, False
+    final = r_old       # what the reference returns when the loop never runs
+    pending = None      # (iteration number, host slot, vector that iteration produced)
     for it in range(limit):
         step(r_old, r_new, partial)
         all_gather_slices(r_new, bounds, group)
-        if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if distributed:
             dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
         step.set_dangling_mass(partial)
-        host = partial.cpu()
-        residual = float(np.sqrt(np.float32(host[0].item())))  # L2 norm of the delta in fp32 (src/pagerank.cu:118)
-        l1 = float(host[1].item())
-        iters = it + 1
+        slot = it % 2
+        host_bufs[slot].copy_(partial, non_blocking=True)
+        if on_gpu:
+            events[slot].record()
+        if pending is not None:
+            p_iter, p_slot, p_vec = pending
+            residual, l1 = read(p_slot)
+            iters, final = p_iter, p_vec
+            if on_iteration is not None:
+                on_iteration(iters, residual)
+            if fixed_iterations <= 0 and residual < tolerance:
+                conv = True
+                pending = None
+                break
+        pending = (it + 1, slot, r_new)
+        r_old, r_new = r_new, r_old
+    if pending is not None:  # the last queued iteration
+        p_iter, p_slot, p_vec = pending
+        residual, l1 = read(p_slot)
+        iters, final = p_iter, p_vec
         if on_iteration is not None:
             on_iteration(iters, residual)
-        if fixed_iterations <= 0 and residual < tolerance:
-            conv, from_new = True, True
-            break
-        if fixed_iterations > 0 and iters == limit:
-            conv, from_new = residual < tolerance, True
-            break
-        r_old, r_new = r_new, r_old
-    return (r_new if from_new else r_old), iters, residual, conv, l1
+        conv = residual < tolerance
+    return final, iters, residual, conv, l1
 
 
 # ------------------------------------------------------- CUDA step (product) ----
