@@ -148,6 +148,11 @@ PROTOTYPES = {
     "spmv_b200_pr_dangling_bits": (C.c_int, [vp, C.c_int, vp, vp]),
     "spmv_b200_pr_init": (C.c_int, [C.c_int, vp, vp, vp, vp]),
     "spmv_b200_pr_step": (C.c_int, [vp, vp, vp, C.c_float, vp, vp, vp, vp]),
+    "spmv_b200_pr_step_p2p": (C.c_int, [vp, vp, vp, C.c_float, vp, vp, vp, C.POINTER(vp), C.c_int, C.c_int, vp]),
+    "spmv_b200_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), C.c_char_p]),
+    "spmv_b200_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "spmv_b200_ipc_close": (C.c_int, [vp]),
+    "spmv_b200_ipc_free": (C.c_int, [vp]),
     "spmv_b200_pr_normalize": (C.c_int, [vp, C.c_int, vp, vp]),
     "spmv_b200_pagerank_device": (C.c_int, [CSR_P, PRC_P, vp, c_int_p, c_float_p, C.POINTER(C.c_bool), c_double_p]),
 }

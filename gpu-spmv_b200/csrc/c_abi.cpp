@@ -385,6 +385,46 @@ int spmv_b200_pr_step(spmv_b200_pr_plan* plan, const float* d_r_old, float* d_r_
                              static_cast<cudaStream_t>(stream));
     });
 }
+int spmv_b200_pr_step_p2p(spmv_b200_pr_plan* plan, const float* d_r_old, float* d_r_new, float damping,
+                          const float* d_dsum, const uint32_t* d_bits, double* d_partial, float* const* peer_r_new,
+                          int n_peers, int self_rank, void* stream) {
+    return guarded([&] {
+        return b200::pr_step(reinterpret_cast<b200::PrPlan*>(plan), d_r_old, d_r_new, damping, d_dsum, d_bits, d_partial,
+                             static_cast<cudaStream_t>(stream), peer_r_new, n_peers, self_rank);
+    });
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+
+int spmv_b200_ipc_alloc(size_t bytes, void** d_ptr, unsigned char handle[64]) {
+    if (!d_ptr || !handle || bytes == 0) return kBadArg;
+    if (cudaMalloc(d_ptr, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return SPMV_B200_CUDA_MALLOC;
+    }
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, *d_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        return SPMV_B200_CUDA_MALLOC;
+    }
+    std::memcpy(handle, &h, 64);
+    return 0;
+}
+int spmv_b200_ipc_open(const unsigned char handle[64], void** d_ptr) {
+    if (!d_ptr || !handle) return kBadArg;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    if (cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return SPMV_B200_CUDA_MALLOC;
+    }
+    return 0;
+}
+int spmv_b200_ipc_close(void* d_ptr) { return cudaIpcCloseMemHandle(d_ptr) == cudaSuccess ? 0 : SPMV_B200_CUDA_MALLOC; }
+int spmv_b200_ipc_free(void* d_ptr) { return cudaFree(d_ptr) == cudaSuccess ? 0 : SPMV_B200_CUDA_MALLOC; }
+
 int spmv_b200_pr_normalize(const float* d_r, int n, float* d_out, void* stream) {
     if (!d_r || !d_out || n < 0) return kBadArg;
     return guarded([&] {

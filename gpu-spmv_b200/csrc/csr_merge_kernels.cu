@@ -121,10 +121,12 @@ struct PlainRow {
     using Sums = NoSums;
     static constexpr bool kReduces = false;
     float* y;
-    __device__ __forceinline__ void prepare() {}
-    __device__ __forceinline__ void finish(int row, float sum, Sums&) const { y[row] = sum; }
+    __device__ __forceinline__ float prepare() const { return 0.0f; }
+    __device__ __forceinline__ void finish(int row, float sum, Sums&, float) const { y[row] = sum; }
     __device__ __forceinline__ void park(int row, float partial) const { y[row] = partial; }
     __device__ __forceinline__ float parked(int row) const { return y[row]; }
+    __device__ __forceinline__ void publish_rows(int, int, int) const {}
+    __device__ __forceinline__ void publish_row(int) const {}
 };
 
 // fused PageRank update of one finished row
@@ -132,12 +134,11 @@ struct PageRankRow {
     using Sums = RankSums;
     static constexpr bool kReduces = true;
     PageRankStepArgs a;
-    float dangling_term;  // d * dsum / n, set by prepare()
-    __device__ __forceinline__ void prepare() {
-        // reference src/pagerank.cu:111: damping * dangling_sum / n, evaluated left to right in fp32
-        dangling_term = __fdiv_rn(__fmul_rn(a.damping, *a.d_dsum), static_cast<float>(a.n_global));
+    // d * dsum / n (reference src/pagerank.cu:111: damping * dangling_sum / n, left to right in fp32)
+    __device__ __forceinline__ float prepare() const {
+        return __fdiv_rn(__fmul_rn(a.damping, *a.d_dsum), static_cast<float>(a.n_global));
     }
-    __device__ __forceinline__ void finish(int row, float sum, Sums& s) const {
+    __device__ __forceinline__ void finish(int row, float sum, Sums& s, float dangling_term) const {
         const int g = a.row_offset + row;
         // reference src/pagerank.cu:113: (damping * y + dangling_contrib) + teleport
         const float v = __fadd_rn(__fadd_rn(__fmul_rn(a.damping, sum), dangling_term), a.teleport);
@@ -149,6 +150,29 @@ struct PageRankRow {
     }
     __device__ __forceinline__ void park(int row, float partial) const { a.r_new[a.row_offset + row] = partial; }
     __device__ __forceinline__ float parked(int row) const { return a.r_new[a.row_offset + row]; }
+    // Fused slice exchange (the "all-gather" of the sharded iteration): after a CTA-wide barrier
+    // the rows [row_lo, row_hi) this tile has just finished are copied from the local r_new
+    // (still in L2) into the r_new buffer of every peer GPU with coalesced stores over NVLink --
+    // one contiguous run per peer instead of one 4-byte packet per row.
+    __device__ __forceinline__ void publish_rows(int row_lo, int row_hi, int tid) const {
+        if (a.n_peers <= 1) return;
+        const int g0 = a.row_offset + row_lo, g1 = a.row_offset + row_hi;
+        const volatile float* src = a.r_new;
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p) {  // static indices: the pointer table stays in the constant bank
+            if (p >= a.n_peers || p == a.self_rank) continue;
+            float* dst = a.peers[p];
+            for (int g = g0 + tid; g < g1; g += kT) dst[g] = src[g];
+        }
+    }
+    __device__ __forceinline__ void publish_row(int row) const {  // a single row finished by the fix-up
+        if (a.n_peers <= 1) return;
+        const int g = a.row_offset + row;
+        const float v = a.r_new[g];
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p < a.n_peers && p != a.self_rank) a.peers[p][g] = v;
+    }
 };
 
 // block-wide sum of RankSums into partials[slot*3 .. +3] (fixed order)
@@ -193,7 +217,7 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
     const int tile_items = tile_rows + tile_nz;
     const int nz_e = c1.y;
 
-    row_op.prepare();
+    const float row_ctx = row_op.prepare();
 
     const int base = nz_s & ~3;
     const bool vec_ok = dev::aligned16(values) && dev::aligned16(col_indices);  // any device pointer is legal
@@ -298,7 +322,7 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
                     first_sum = running;
                     first_row = r;
                 } else {
-                    row_op.finish(row_s + r, running, sums);
+                    row_op.finish(row_s + r, running, sums, row_ctx);
                 }
                 running = 0.0f;
                 ++r;
@@ -341,7 +365,7 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
     if (emitted) {
         const float total = carry_in + first_sum;
         if (first_row == 0 && first_row_split) row_op.park(row_s, total);  // level 3 finishes it
-        else row_op.finish(row_s + first_row, total, sums);
+        else row_op.finish(row_s + first_row, total, sums, row_ctx);
     }
 
     // ---- tile carry-out: the row still open at the tile end ------------------------
@@ -354,7 +378,11 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
         carry_val[tile] = has_open ? open_sum : 0.0f;
     }
 
-    if (Row::kReduces) block_store_sums(sums, partials, tile, s_sums);
+    if (Row::kReduces) {
+        __syncthreads();  // every finish() store of this CTA is visible CTA-wide
+        row_op.publish_rows(row_s + (first_row_split ? 1 : 0), c1.x, tid);
+        block_store_sums(sums, partials, tile, s_sums);
+    }
 }
 
 // ---------------------------------------------------------------- level 3 ----
@@ -367,14 +395,15 @@ merge_fixup_kernel(int num_tiles, const int* __restrict__ carry_row, const float
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     typename Row::Sums sums;
     sums.clear();
-    row_op.prepare();
+    const float row_ctx = row_op.prepare();
     if (t < num_tiles) {
         const int row = carry_row[t];
         if (row >= 0 && (t == 0 || carry_row[t - 1] != row)) {  // leader of a run of tiles
             float total = carry_val[t];
             for (int u = t + 1; u < num_tiles && carry_row[u] == row; ++u) total += carry_val[u];
             // the tile in which the row ends parked its own share
-            row_op.finish(row, row_op.parked(row) + total, sums);
+            row_op.finish(row, row_op.parked(row) + total, sums, row_ctx);
+            row_op.publish_row(row);
         }
     }
     if (Row::kReduces) block_store_sums(sums, partials, num_tiles + blockIdx.x, s_sums);
@@ -450,7 +479,7 @@ cudaError_t launch_merge_pagerank(const CsrView& A, const MergePlan& plan, const
         cudaError_t e = cudaMemsetAsync(args.out, 0, 3 * sizeof(double), stream);
         return e;
     }
-    PageRankRow op{args, 0.0f};
+    PageRankRow op{args};
     cudaError_t e = run_tiles(A, args.r_old, plan, op, stream);
     if (e != cudaSuccess) return e;
     reduce_partials_kernel<<<1, 1024, 0, stream>>>(plan.partials, plan.num_tiles + plan.fixup_blocks, args.out);

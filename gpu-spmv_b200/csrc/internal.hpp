@@ -78,6 +78,7 @@ size_t merge_plan_bytes(int rows, int nnz, bool with_partials);
 MergePlan merge_plan_carve(void* block, int rows, int nnz, bool with_partials);
 
 // ---- fused PageRank epilogue parameters ---------------------------------------------
+constexpr int kMaxPeers = 8;  // GPUs of one NVSwitch box
 struct PageRankStepArgs {
     const float* r_old;     // full vector [n_global]
     float* r_new;           // full vector [n_global]
@@ -88,6 +89,12 @@ struct PageRankStepArgs {
     const float* d_dsum;    // device scalar: dangling mass of r_old
     const uint32_t* bits;   // dangling bitmask over global node ids
     double* out;            // device [3]: sum d^2, sum |d|, next dangling mass
+    // fused slice exchange: when n_peers > 1 every finished rank value is also stored into the
+    // r_new buffer of every other rank (peer-mapped device pointers, NVLink), so no all-gather
+    // follows the step.  peers[self_rank] is ignored (r_new is the local buffer).
+    float* peers[kMaxPeers];
+    int n_peers;
+    int self_rank;
 };
 
 // ---- kernel launchers (stream-ordered; return the launch status) --------------------
@@ -141,7 +148,8 @@ struct PrPlan;
 int pr_plan_create(const CSRMatrix* shard, int row_offset, int n_global, cudaStream_t stream, PrPlan** out);
 void pr_plan_destroy(PrPlan* plan);
 int pr_step(PrPlan* plan, const float* d_r_old, float* d_r_new, float damping, const float* d_dsum,
-            const uint32_t* d_bits, double* d_partial, cudaStream_t stream);
+            const uint32_t* d_bits, double* d_partial, cudaStream_t stream,
+            float* const* peer_r_new = nullptr, int n_peers = 0, int self_rank = 0);
 const CsrView& pr_plan_view(const PrPlan* plan);
 double* pr_plan_tmp(PrPlan* plan);
 int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,

@@ -118,8 +118,9 @@ def pagerank_loop(step, r_old, r_new, partial, bounds, damping, tolerance, max_i
     pending = None      # (iteration number, host slot, vector that iteration produced)
     for it in range(limit):
         step(r_old, r_new, partial)
-        all_gather_slices(r_new, bounds, group)
-        if distributed:
+        if not getattr(step, "delivers_slices", False):
+            all_gather_slices(r_new, bounds, group)
+        if distributed:  # with a fused exchange this all-reduce is also the barrier that orders the peer stores
             dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
         step.set_dangling_mass(partial)
         slot = it % 2
@@ -150,6 +151,17 @@ def pagerank_loop(step, r_old, r_new, partial, bounds, damping, tolerance, max_i
 
 # ------------------------------------------------------- CUDA step (product) ----
 
+class _RawDeviceArray:
+    """float32 device memory owned by libspmv_b200 (cudaMalloc), exposed to torch without a copy."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _tensor_from_ptr(ptr, n, device):
+    return torch.as_tensor(_RawDeviceArray(ptr, n), device=device)
+
+
 class CudaShard:
     """This rank's row shard on its GPU plus the fused-iteration plan."""
 
@@ -168,6 +180,7 @@ class CudaShard:
         self.bits = torch.zeros((self.n + 31) // 32, dtype=torch.int32, device=self.dev)
         self.dsum = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.damping = 0.85
+        self._peer_tables, self._world, self._rank = {}, 1, 0
 
     def _s(self):
         return C.c_void_p(self.stream if self.stream is not None else torch.cuda.current_stream().cuda_stream)
@@ -192,10 +205,63 @@ class CudaShard:
         assert rc == 0
 
     def __call__(self, r_old, r_new, partial):
-        rc = sp.lib.spmv_b200_pr_step(self.plan, sp.dptr(r_old), sp.dptr(r_new), self.damping, sp.dptr(self.dsum),
-                                      sp.dptr(self.bits), sp.dptr(partial), self._s())
+        table = self._peer_tables.get(r_new.data_ptr()) if self._peer_tables else None
+        if table is not None:  # slice exchange fused into the step (peer stores over NVLink)
+            rc = sp.lib.spmv_b200_pr_step_p2p(self.plan, sp.dptr(r_old), sp.dptr(r_new), self.damping,
+                                              sp.dptr(self.dsum), sp.dptr(self.bits), sp.dptr(partial), table,
+                                              self._world, self._rank, self._s())
+        else:
+            rc = sp.lib.spmv_b200_pr_step(self.plan, sp.dptr(r_old), sp.dptr(r_new), self.damping, sp.dptr(self.dsum),
+                                          sp.dptr(self.bits), sp.dptr(partial), self._s())
         if rc != 0:
             raise RuntimeError(f"pr_step: {sp.spmv_error_string(rc)}")
+
+    # ---- fused slice exchange: peer-mapped rank-vector buffers ---------------------------------
+    @property
+    def delivers_slices(self):
+        """True when the step itself writes this rank's slice into every peer's vector."""
+        return bool(self._peer_tables)
+
+    def enable_peer_exchange(self, group=None):
+        """Allocates the two rank-vector buffers of the iteration as CUDA-IPC shareable memory,
+        maps every peer's pair into this process and returns them as torch tensors (r_a, r_b).
+        Needs one process per GPU on one NVLink/NVSwitch box."""
+        self._world, self._rank = dist.get_world_size(group), dist.get_rank(group)
+        if self._world > 8:
+            raise ValueError("peer exchange is for the <= 8 GPUs of one box")
+        nbytes = self.n * 4
+        mine, handles = [], []
+        for _ in range(2):
+            ptr, h = C.c_void_p(), C.create_string_buffer(64)
+            rc = sp.lib.spmv_b200_ipc_alloc(nbytes, C.byref(ptr), h)
+            if rc != 0:
+                raise RuntimeError(f"ipc_alloc: {sp.spmv_error_string(rc)}")
+            mine.append(ptr.value)
+            handles.append(h.raw)
+        everyone = [None] * self._world
+        dist.all_gather_object(everyone, handles, group=group)
+        self._ipc_mine, self._ipc_opened, self._peer_tables = mine, [], {}
+        for b in range(2):
+            table = (C.c_void_p * 8)()
+            for p in range(self._world):
+                if p == self._rank:
+                    table[p] = mine[b]
+                else:
+                    ptr = C.c_void_p()
+                    rc = sp.lib.spmv_b200_ipc_open(everyone[p][b], C.byref(ptr))
+                    if rc != 0:
+                        raise RuntimeError(f"ipc_open (rank {p}): {sp.spmv_error_string(rc)}")
+                    table[p] = ptr.value
+                    self._ipc_opened.append(ptr.value)
+            self._peer_tables[mine[b]] = table
+        return tuple(_tensor_from_ptr(ptr, self.n, self.dev) for ptr in mine)
+
+    def disable_peer_exchange(self):
+        for ptr in getattr(self, "_ipc_opened", []):
+            sp.lib.spmv_b200_ipc_close(C.c_void_p(ptr))
+        for ptr in getattr(self, "_ipc_mine", []):
+            sp.lib.spmv_b200_ipc_free(C.c_void_p(ptr))
+        self._ipc_opened, self._ipc_mine, self._peer_tables = [], [], {}
 
     def set_dangling_mass(self, partial):
         self.dsum.copy_(partial[2:3].to(torch.float32))
@@ -213,13 +279,17 @@ class CudaShard:
 
 
 def pagerank_sharded(shard, bounds, damping=0.85, tolerance=1e-6, max_iterations=100, group=None,
-                     fixed_iterations=0):
+                     fixed_iterations=0, fused_exchange=False):
     """PageRank over row shards, one CudaShard per rank; returns a PageRankOutcome whose
-    ranks tensor (full length, normalised) is identical on every rank."""
+    ranks tensor (full length, normalised) is identical on every rank.  fused_exchange=True
+    replaces the NCCL all-gather by peer stores from inside the step kernel."""
     shard.damping = float(damping)
     shard.setup_dangling(group)
-    r_a = torch.empty(shard.n, dtype=torch.float32, device=shard.dev)
-    r_b = torch.empty_like(r_a)
+    if fused_exchange and dist.is_initialized() and dist.get_world_size(group) > 1:
+        r_a, r_b = shard.enable_peer_exchange(group)
+    else:
+        r_a = torch.empty(shard.n, dtype=torch.float32, device=shard.dev)
+        r_b = torch.empty_like(r_a)
     partial = torch.zeros(3, dtype=torch.float64, device=shard.dev)
     shard.init_vector(r_a)
     fin, iters, residual, conv, l1 = pagerank_loop(shard, r_a, r_b, partial, bounds, damping, tolerance,

@@ -308,6 +308,26 @@ SPMV_B200_API int spmv_b200_pr_init(int n, const uint32_t* d_bits, float* d_r, f
 SPMV_B200_API int spmv_b200_pr_step(spmv_b200_pr_plan* plan, const float* d_r_old, float* d_r_new,
                                     float damping, const float* d_dsum, const uint32_t* d_bits,
                                     double* d_partial /* [3] */, void* stream);
+/*
+ * The same step with the slice exchange FUSED into it (one process per GPU on an
+ * NVLink/NVSwitch box): peer_r_new is a host array of n_peers device pointers, entry p being
+ * rank p's r_new buffer mapped into this process (spmv_b200_ipc_open); every finished rank value
+ * is stored into all of them from inside the kernel, tile by tile, so no all-gather follows.
+ * The caller must order the next iteration after all ranks' steps (the all-reduce of d_partial
+ * does that).  n_peers <= 8.
+ */
+SPMV_B200_API int spmv_b200_pr_step_p2p(spmv_b200_pr_plan* plan, const float* d_r_old, float* d_r_new,
+                                        float damping, const float* d_dsum, const uint32_t* d_bits,
+                                        double* d_partial, float* const* peer_r_new, int n_peers,
+                                        int self_rank, void* stream);
+
+/* Device buffers that other processes of the box can map (CUDA IPC): alloc returns the device
+ * pointer and a 64-byte handle to send to the peers; open maps a peer's handle. */
+SPMV_B200_API int spmv_b200_ipc_alloc(size_t bytes, void** d_ptr, unsigned char handle[64]);
+SPMV_B200_API int spmv_b200_ipc_open(const unsigned char handle[64], void** d_ptr);
+SPMV_B200_API int spmv_b200_ipc_close(void* d_ptr);
+SPMV_B200_API int spmv_b200_ipc_free(void* d_ptr);
+
 /* d_out[i] = d_r[i] / (float)sum(d_r) over n elements (f64 sum) */
 SPMV_B200_API int spmv_b200_pr_normalize(const float* d_r, int n, float* d_out, void* stream);
 
