@@ -232,7 +232,7 @@ def build_rmat_shard(torch, gen, scale, edge_factor, seed, rank, world, device, 
     row_ptrs = torch.zeros(n + 1, dtype=torch.int64, device=device)
     row_ptrs[1:] = torch.cumsum(indeg, dim=0)
     import gpu_spmv_b200.dist as D
-    bounds = D.partition_rows(row_ptrs.to(torch.int32) if n_edges < 2 ** 31 else row_ptrs, world)
+    bounds = D.partition_rows(row_ptrs, world, row_weight=1)  # balance merge items (rows + nnz)
     r_lo, r_hi = bounds[rank], bounds[rank + 1]
     keys = []
     for lo in range(0, n_edges, chunk):
@@ -416,39 +416,51 @@ def run_product_arm(args):
         if do_pagerank:
             # fixed number of iterations of the sharded loop (stop rule evaluated every iteration,
             # one iteration late), wall clock around the loop after a device sync, max over ranks
-            log(f"R-MAT scale {scale}: PageRank")
             shard.damping = 0.85
+            modes = ["p2p", "nccl"] if dist_on else ["single"]
             with torch.cuda.stream(stream):
                 shard.setup_dangling()
-                r_a = torch.empty(n, dtype=torch.float32, device=dev)
-                r_b = torch.empty_like(r_a)
-                partial = torch.zeros(3, dtype=torch.float64, device=dev)
-                shard.init_vector(r_a)
-                D.pagerank_loop(shard, r_a, r_b, partial, bounds, 0.85, 0.0, 0, fixed_iterations=3)  # warm-up
-                shard.init_vector(r_a)
+            for mode in modes:
+                log(f"R-MAT scale {scale}: PageRank ({mode})")
+                with torch.cuda.stream(stream):
+                    if mode == "p2p":
+                        r_a, r_b = shard.enable_peer_exchange()
+                    else:
+                        r_a = torch.empty(n, dtype=torch.float32, device=dev)
+                        r_b = torch.empty_like(r_a)
+                    partial = torch.zeros(3, dtype=torch.float64, device=dev)
+                    shard.init_vector(r_a)
+                    D.pagerank_loop(shard, r_a, r_b, partial, bounds, 0.85, 0.0, 0, fixed_iterations=3)  # warm-up
+                    shard.init_vector(r_a)
+                    if dist_on:
+                        dist.barrier()
+                    torch.cuda.synchronize()
+                    iters = args.pr_iters
+                    t0 = time.perf_counter()
+                    fin, done, residual, conv, l1 = D.pagerank_loop(shard, r_a, r_b, partial, bounds, 0.85, 0.0, 0,
+                                                                    fixed_iterations=iters)
+                    torch.cuda.synchronize()
+                    sec = time.perf_counter() - t0
                 if dist_on:
+                    t = torch.tensor([sec], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    sec = float(t.item())
                     dist.barrier()
-                torch.cuda.synchronize()
-                iters = args.pr_iters
-                t0 = time.perf_counter()
-                fin, done, residual, conv, l1 = D.pagerank_loop(shard, r_a, r_b, partial, bounds, 0.85, 0.0, 0,
-                                                                fixed_iterations=iters)
-                torch.cuda.synchronize()
-                sec = time.perf_counter() - t0
-            if dist_on:
-                t = torch.tensor([sec], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                sec = float(t.item())
-            it_bytes = float(tot4.item())
-            extra["pagerank"] = {"iters_per_s": iters / sec, "ms_per_iter": sec / iters * 1e3,
-                                 "graph": f"R-MAT scale {scale} x16, d=0.85", "n": n, "nnz": n_edges,
-                                 "iterations_timed": iters, "l2_residual_after": residual,
-                                 "effective_gbs": it_bytes / (sec / iters) / 1e9, "scaling": "strong",
-                                 "frac_of_measured_peak": it_bytes / (sec / iters) / 1e9 / world / peak,
-                                 "collectives": ("all-gather of rank slices + all-reduce of 3 f64 (NCCL)" if dist_on
-                                                 else "none (1 GPU)"),
-                                 "includes": "fused step + collectives + lagged host read of the residual every iteration; "
-                                             "excluded: setup + final normalisation"}
+                if mode == "p2p":
+                    shard.disable_peer_exchange()
+                it_bytes = float(tot4.item())
+                exchange = {"p2p": "fused into the step kernel: peer stores of finished rows over NVLink (CUDA IPC) "
+                                   "+ NCCL all-reduce of 3 f64",
+                            "nccl": "NCCL all-gather of the rank slices + all-reduce of 3 f64",
+                            "single": "none (1 GPU)"}[mode]
+                extra["pagerank" if mode != "nccl" else "pagerank_nccl_allgather"] = {
+                    "iters_per_s": iters / sec, "ms_per_iter": sec / iters * 1e3,
+                    "graph": f"R-MAT scale {scale} x16, d=0.85", "n": n, "nnz": n_edges, "iterations_timed": iters,
+                    "l2_residual_after": residual, "effective_gbs": it_bytes / (sec / iters) / 1e9, "scaling": "strong",
+                    "frac_of_measured_peak": it_bytes / (sec / iters) / 1e9 / world / peak, "exchange": exchange,
+                    "includes": "fused step + exchange + lagged host read of the residual every iteration; "
+                                "excluded: setup + final normalisation"}
+                del r_a, r_b
         shard.close()
         del shard, srp, sci, sva, xg, yg
         torch.cuda.empty_cache()

@@ -443,10 +443,11 @@ def merge_path_search(diagonal, row_ptrs, num_rows, nnz):
     return r.value, z.value
 
 
-def partition_rows(row_ptrs, num_rows, parts):
+def partition_rows(row_ptrs, num_rows, parts, row_weight=0):
+    """Contiguous row split balancing nnz(row) + row_weight (0: nnz-balanced, 1: merge items)."""
     _keep, p = _i32(row_ptrs)
     bounds = np.zeros(parts + 1, dtype=np.int32)
-    rc = lib.spmv_b200_partition_rows(p, num_rows, parts, bounds.ctypes.data_as(capi.c_int_p))
+    rc = lib.spmv_b200_partition_rows_weighted(p, num_rows, parts, int(row_weight), bounds.ctypes.data_as(capi.c_int_p))
     if rc != 0:
         raise ValueError(spmv_error_string(rc))
     return bounds

@@ -142,6 +142,7 @@ PROTOTYPES = {
     "spmv_b200_ell_from_csr_device": (C.c_int, [ELL_P, CSR_P]),
     "spmv_b200_merge_path_search": (C.c_int, [C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p]),
     "spmv_b200_partition_rows": (C.c_int, [c_int_p, C.c_int, C.c_int, c_int_p]),
+    "spmv_b200_partition_rows_weighted": (C.c_int, [c_int_p, C.c_int, C.c_int, C.c_int, c_int_p]),
     "spmv_b200_pr_plan_create": (C.c_int, [CSR_P, C.c_int, C.c_int, vp, C.POINTER(vp)]),
     "spmv_b200_pr_plan_destroy": (None, [vp]),
     "spmv_b200_pr_colsum": (C.c_int, [vp, vp, vp]),

@@ -327,24 +327,29 @@ int spmv_b200_merge_path_search(int diagonal, const int* row_ptrs, int num_rows,
     return 0;
 }
 
-// nnz-balanced contiguous row split: bounds[p] = first row whose start offset
-// is >= p * nnz / parts.
-int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, int parts, int* bounds) {
-    if (!row_ptrs || !bounds || num_rows < 0 || parts <= 0) return kBadArg;
-    const long long nnz = row_ptrs[num_rows];
+// Contiguous row split balancing work(row) = nnz(row) + row_weight: bounds[p] = first row whose
+// prefix work (row_ptrs[i] + i * row_weight) is >= p * total / parts.
+int spmv_b200_partition_rows_weighted(const int* row_ptrs, int num_rows, int parts, int row_weight, int* bounds) {
+    if (!row_ptrs || !bounds || num_rows < 0 || parts <= 0 || row_weight < 0) return kBadArg;
+    const long long total = static_cast<long long>(row_ptrs[num_rows]) + static_cast<long long>(num_rows) * row_weight;
     bounds[0] = 0;
     for (int p = 1; p < parts; ++p) {
-        const long long target = nnz * p / parts;
+        const long long target = total * p / parts;
         int lo = 0, hi = num_rows;
         while (lo < hi) {
             const int mid = lo + ((hi - lo) >> 1);
-            if (row_ptrs[mid] < target) lo = mid + 1;
+            if (row_ptrs[mid] + static_cast<long long>(mid) * row_weight < target) lo = mid + 1;
             else hi = mid;
         }
         bounds[p] = lo < bounds[p - 1] ? bounds[p - 1] : lo;
     }
     bounds[parts] = num_rows;
     return 0;
+}
+
+// nnz-balanced split (row_weight 0)
+int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, int parts, int* bounds) {
+    return spmv_b200_partition_rows_weighted(row_ptrs, num_rows, parts, 0, bounds);
 }
 
 int spmv_b200_pr_plan_create(const spmv_b200_csr* shard, int row_offset, int n_global, void* stream,

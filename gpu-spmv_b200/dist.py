@@ -27,21 +27,22 @@ import gpu_spmv_b200 as sp
 
 # ------------------------------------------------------------- partitioning ----
 
-def partition_rows(row_ptrs, parts):
-    """nnz-balanced contiguous row split; row_ptrs is a host int32 array or a
-    torch tensor (any device).  Returns a list of parts+1 row bounds."""
+def partition_rows(row_ptrs, parts, row_weight=0):
+    """Contiguous row split balancing work(row) = nnz(row) + row_weight (0: nnz-balanced; 1: the
+    merge-path items rows + nnz that the merge-path / PageRank kernels consume).  row_ptrs is a
+    host int32 array or a torch tensor (any device).  Returns a list of parts+1 row bounds."""
     if torch.is_tensor(row_ptrs) and row_ptrs.is_cuda:
         rows = row_ptrs.numel() - 1
-        nnz = int(row_ptrs[-1].item())
-        targets = torch.tensor([(nnz * p) // parts for p in range(1, parts)], dtype=row_ptrs.dtype,
-                               device=row_ptrs.device)
-        inner = torch.searchsorted(row_ptrs[:rows].contiguous(), targets, right=False).tolist() if parts > 1 else []
+        prefix = row_ptrs[:rows].to(torch.int64) + torch.arange(rows, dtype=torch.int64, device=row_ptrs.device) * row_weight
+        total = int(row_ptrs[-1].item()) + rows * row_weight
+        targets = torch.tensor([(total * p) // parts for p in range(1, parts)], dtype=torch.int64, device=row_ptrs.device)
+        inner = torch.searchsorted(prefix, targets, right=False).tolist() if parts > 1 else []
         bounds = [0] + [int(b) for b in inner] + [rows]
         for p in range(1, parts + 1):
             bounds[p] = max(bounds[p], bounds[p - 1])
         return bounds
     rp = np.ascontiguousarray(row_ptrs.numpy() if torch.is_tensor(row_ptrs) else row_ptrs, dtype=np.int32)
-    return [int(b) for b in sp.partition_rows(rp, len(rp) - 1, parts)]
+    return [int(b) for b in sp.partition_rows(rp, len(rp) - 1, parts, row_weight)]
 
 
 def extract_shard(row_ptrs, col_indices, values, lo, hi):

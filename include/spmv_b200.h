@@ -274,6 +274,10 @@ SPMV_B200_API int spmv_b200_merge_path_search(int diagonal, const int* row_ptrs,
                                               int nnz, int* out_row, int* out_nz);
 SPMV_B200_API int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, int parts,
                                            int* bounds /* [parts+1] */);
+/* the same split with the work of a row counted as nnz + row_weight (row_weight = 1 balances the
+ * merge-path items rows + nnz, which is what the merge-path / PageRank kernels consume) */
+SPMV_B200_API int spmv_b200_partition_rows_weighted(const int* row_ptrs, int num_rows, int parts,
+                                                    int row_weight, int* bounds /* [parts+1] */);
 
 /* ---- device-resident PageRank building blocks --------------------------- */
 

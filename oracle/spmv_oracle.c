@@ -494,20 +494,21 @@ ORC_API void orc_merge_path_search(int diagonal, const int *row_ptrs, int rows, 
 }
 
 /*
- * nnz-balanced contiguous row split: boundary p is the first row
- * whose start offset is >= p*nnz/parts (lower_bound on row_ptrs), with
- * bounds[0]=0 and bounds[parts]=rows.
+ * Contiguous row split: boundary p is the first row whose prefix
+ * work row_ptrs[i] + i*row_weight is >= p*total/parts (lower_bound), with
+ * bounds[0]=0 and bounds[parts]=rows.  row_weight 0 = nnz-balanced, 1 =
+ * (rows + nnz)-balanced, the coarse level of the merge-path search.
  */
-ORC_API void orc_partition_rows(int rows, const int *row_ptrs, int parts, int *bounds)
+ORC_API void orc_partition_rows_weighted(int rows, const int *row_ptrs, int parts, int row_weight, int *bounds)
 {
-    int64_t nnz = row_ptrs[rows];
+    int64_t total = (int64_t)row_ptrs[rows] + (int64_t)rows * row_weight;
     bounds[0] = 0;
     for (int p = 1; p < parts; p++) {
-        int64_t target = (nnz * p) / parts;
+        int64_t target = (total * p) / parts;
         int lo = 0, hi = rows;
         while (lo < hi) {
             int mid = lo + (hi - lo) / 2;
-            if ((int64_t)row_ptrs[mid] < target) lo = mid + 1;
+            if ((int64_t)row_ptrs[mid] + (int64_t)mid * row_weight < target) lo = mid + 1;
             else hi = mid;
         }
         bounds[p] = lo;
@@ -515,6 +516,11 @@ ORC_API void orc_partition_rows(int rows, const int *row_ptrs, int parts, int *b
     bounds[parts] = rows;
     for (int p = 1; p <= parts; p++)
         if (bounds[p] < bounds[p - 1]) bounds[p] = bounds[p - 1];
+}
+
+ORC_API void orc_partition_rows(int rows, const int *row_ptrs, int parts, int *bounds)
+{
+    orc_partition_rows_weighted(rows, row_ptrs, parts, 0, bounds);
 }
 
 /* ------------------------------------------------------------------ */

@@ -189,9 +189,9 @@ class Oracle:
         self.L.orc_merge_path_search(diagonal, _i(i32(rp)), rows, nnz, C.byref(r), C.byref(z))
         return r.value, z.value
 
-    def partition_rows(self, rows, rp, parts):
+    def partition_rows(self, rows, rp, parts, row_weight=0):
         b = np.zeros(parts + 1, np.int32)
-        self.L.orc_partition_rows(rows, _i(i32(rp)), parts, _i(b))
+        self.L.orc_partition_rows_weighted(rows, _i(i32(rp)), parts, row_weight, _i(b))
         return b
 
     def fnv(self, arr):

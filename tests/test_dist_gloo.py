@@ -125,6 +125,10 @@ def test_partition_properties(sp, orc):
         rp = np.zeros(rows + 1, np.int32)
         rp[1:] = np.cumsum(lens)
         for parts in (1, 2, 3, 8):
+            for w in (1, 3):  # (rows + nnz)-balanced variants match the oracle and stay monotone
+                bw = sp.partition_rows(rp, rows, parts, w)
+                assert bw[0] == 0 and bw[-1] == rows and np.all(np.diff(bw) >= 0)
+                assert np.array_equal(bw, orc.partition_rows(rows, rp, parts, w))
             b = sp.partition_rows(rp, rows, parts)
             assert b[0] == 0 and b[-1] == rows and np.all(np.diff(b) >= 0)
             assert np.array_equal(b, orc.partition_rows(rows, rp, parts))
