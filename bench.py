@@ -203,7 +203,7 @@ def bench_kernel(torch, sp, stream, launch, bytes_per_launch, steps, warmup, dis
     return {"ms_per_step": per, "gbs": world * bytes_per_launch / (per * 1e-3) / 1e9}
 
 
-def build_rmat_shard(torch, gen, scale, edge_factor, seed, rank, world, device, chunk=1 << 24):
+def build_rmat_shard(torch, gen, scale, edge_factor, seed, rank, world, device, chunk=1 << 24, row_weight=1):
     """This rank's row shard of the column-normalised R-MAT matrix without materialising the
     whole graph: pass 1 counts in/out degrees of every edge (bincount), pass 2 keeps the edges
     whose destination falls in this rank's nnz-balanced row range and sorts only those."""
@@ -232,7 +232,7 @@ def build_rmat_shard(torch, gen, scale, edge_factor, seed, rank, world, device, 
     row_ptrs = torch.zeros(n + 1, dtype=torch.int64, device=device)
     row_ptrs[1:] = torch.cumsum(indeg, dim=0)
     import gpu_spmv_b200.dist as D
-    bounds = D.partition_rows(row_ptrs, world, row_weight=1)  # balance merge items (rows + nnz)
+    bounds = D.partition_rows(row_ptrs, world, row_weight=row_weight)  # work(row) = nnz + row_weight
     r_lo, r_hi = bounds[rank], bounds[rank + 1]
     keys = []
     for lo in range(0, n_edges, chunk):
@@ -361,7 +361,7 @@ def run_product_arm(args):
 
     # ---- extra: the CSR kernels on config 2 -----------------------------------------------------
     log("config 2: CSR kernels")
-    if not args.quick:
+    if not args.quick and not args.only_pagerank:
         for kernel, name in ((sp.VECTOR_CSR, "csr_vector"), (sp.SCALAR_CSR, "csr_scalar"), (sp.MERGE_PATH, "csr_merge")):
             cfg = sp.make_config(kernel)
             r = bench_kernel(torch, sp, stream, lambda: sp.lib.spmv_b200_spmv_csr_async(
@@ -373,7 +373,7 @@ def run_product_arm(args):
     del A, rp, ci, va, x, y, x_host, y_host
     torch.cuda.empty_cache()
 
-    if not args.quick and world == 1:
+    if not args.quick and not args.only_pagerank and world == 1:
         # ---- config 3: short rows + 4 outlier rows of 1 M nnz: scalar (reference policy) vs merge ---
         log("config 3")
         rows3 = args.c3_rows
@@ -395,7 +395,11 @@ def run_product_arm(args):
     # ---- config 4 / 5: R-MAT SpMV (merge-path) and PageRank, row-sharded over the ranks -----------
     def rmat_section(scale, seed, do_vector, do_pagerank):
         log(f"R-MAT scale {scale}: build")
-        n, bounds, srp, sci, sva, n_edges = build_rmat_shard(torch, gen, scale, 16, seed, rank, world, dev)
+        # SpMV shards balance the merge items (rows + nnz); PageRank shards also pay 4 bytes per
+        # owned row to every peer, so rows weigh more there (tuned on 8 GPUs, profiles/)
+        weight = args.row_weight if args.row_weight >= 0 else (1 if not do_pagerank or world == 1 else 8)
+        n, bounds, srp, sci, sva, n_edges = build_rmat_shard(torch, gen, scale, 16, seed, rank, world, dev,
+                                                            row_weight=weight)
         torch.cuda.synchronize()
         shard = D.CudaShard(n, bounds[rank], srp, sci, sva, stream=s_ptr)
         xg = torch.full((n,), 1.0 / n, dtype=torch.float32, device=dev)
@@ -458,6 +462,7 @@ def run_product_arm(args):
                     "graph": f"R-MAT scale {scale} x16, d=0.85", "n": n, "nnz": n_edges, "iterations_timed": iters,
                     "l2_residual_after": residual, "effective_gbs": it_bytes / (sec / iters) / 1e9, "scaling": "strong",
                     "frac_of_measured_peak": it_bytes / (sec / iters) / 1e9 / world / peak, "exchange": exchange,
+                    "partition": f"work(row) = nnz + {weight}", "rows_per_rank_max": int(max(bounds[i + 1] - bounds[i] for i in range(world))),
                     "includes": "fused step + exchange + lagged host read of the residual every iteration; "
                                 "excluded: setup + final normalisation"}
                 del r_a, r_b
@@ -465,10 +470,12 @@ def run_product_arm(args):
         del shard, srp, sci, sva, xg, yg
         torch.cuda.empty_cache()
 
-    if not args.quick:
+    if not args.quick and not args.only_pagerank:
         rmat_section(args.rmat_scale, 44, do_vector=(world == 1), do_pagerank=(args.pr_scale == args.rmat_scale))
         if args.pr_scale != args.rmat_scale:
             rmat_section(args.pr_scale, 45, do_vector=False, do_pagerank=True)
+    if args.only_pagerank:
+        rmat_section(args.pr_scale, 45, do_vector=False, do_pagerank=True)
 
     if rank == 0:
         roofline = {"bound": "hbm", "achieved": launch_gbs, "peak": peak, "unit": "GB/s", "frac": launch_gbs / peak,
@@ -503,6 +510,8 @@ def main():
     ap.add_argument("--pr-scale", type=int, default=26, help="BASELINE config 5: PageRank graph")
     ap.add_argument("--c3-rows", type=int, default=50_000_000)
     ap.add_argument("--pr-iters", type=int, default=20)
+    ap.add_argument("--row-weight", type=int, default=-1, help="partition work(row) = nnz + row_weight (-1: default policy)")
+    ap.add_argument("--only-pagerank", action="store_true", help="tuning aid: headline + PageRank section only")
     ap.add_argument("--ncu-traffic", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture")
     args = ap.parse_args()

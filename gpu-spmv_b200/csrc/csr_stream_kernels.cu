@@ -243,8 +243,55 @@ struct PipeStageHeader {
     int base;         // non-zero index held by slot 0 of the stage
     int staged_end;   // non-zeros [base, staged_end) are in shared memory
     int rp_staged;    // row_ptrs of the window are in shared memory
-    int pad;
+    int overflow;     // the window holds more non-zeros than a stage: cooperative multi-pass path
 };
+
+// Overflow path of csr_pipe_kernel (a window whose non-zero span does not fit a stage, e.g. a
+// row-owner kernel forced onto a matrix with very long rows): the whole CTA streams the span in
+// passes of 2*cap products through the stage's buffer and the row owners accumulate across
+// passes.  Per row the products are still added in index order, so LPR == 1 stays sequential.
+// Kept out of line so that its registers do not burden the common path.
+template <int LPR>
+__device__ __noinline__ void pipe_overflow_window(int nr, int r0, int rows_per_group, const int* __restrict__ row_ptrs,
+                                                  const int* __restrict__ col_indices, const float* __restrict__ values,
+                                                  const float* __restrict__ x, float* __restrict__ y, int* s_rp,
+                                                  bool rp_staged, float* s_prod, float* s_acc, int prod_cap) {
+    // running sums live in shared memory (s_acc[row]), not registers: this path must not raise
+    // the register count of the kernel it is called from
+    constexpr int kGroups = kThreads / LPR;
+    const int tid = threadIdx.x, group = tid / LPR, lane = tid % LPR;
+    if (!rp_staged) {
+        for (int i = tid; i <= nr; i += kThreads) s_rp[i] = row_ptrs[r0 + i];
+    }
+    for (int i = tid; i < nr * LPR; i += kThreads) s_acc[i] = 0.0f;  // one slot per (row, lane)
+    __syncthreads();
+    const int n0 = s_rp[0], n1 = s_rp[nr];
+    for (int base = n0; base < n1; base += prod_cap) {
+        const int hi = min(base + prod_cap, n1);
+        for (int j = base + tid; j < hi; j += kThreads)
+            s_prod[j - base] = __fmul_rn(dev::ld_stream_f(values + j), dev::ld_x(x + dev::ld_stream_i(col_indices + j)));
+        __syncthreads();
+        for (int i = 0; i < rows_per_group; ++i) {
+            const int r = group + i * kGroups;
+            if (r < nr) {
+                const int a = max(s_rp[r], base), b = min(s_rp[r + 1], hi);
+                if (a < b) {
+                    float t = s_acc[r * LPR + lane];
+                    for (int j = a + lane; j < b; j += LPR) t = __fadd_rn(t, s_prod[j - base]);
+                    s_acc[r * LPR + lane] = t;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = 0; i < rows_per_group; ++i) {
+        const int r = group + i * kGroups;
+        float t = r < nr ? s_acc[r * LPR + lane] : 0.0f;
+#pragma unroll
+        for (int d = LPR / 2; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d, LPR);
+        if (lane == 0 && r < nr) y[r0 + r] = t;
+    }
+}
 
 template <int LPR, int U>
 __global__ void __launch_bounds__(kThreads)
@@ -273,13 +320,15 @@ csr_pipe_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* 
         const int r0 = w * window_rows;
         const int base = n0 & ~3;
         int end = min((n1 + 3) & ~3, nnz & ~3);
-        end = min(end, base + cap);
+        const bool overflow = end - base > cap;  // does not fit a stage: nothing is staged, see pipe_overflow_window
+        if (overflow) end = base;
         end = max(end, base);
         const bool rp_ok = r0 + window_rows + 4 <= rows + 1;
         PipeStageHeader* h = stage_header(s);
         h->base = base;
         h->staged_end = end;
         h->rp_staged = rp_ok ? 1 : 0;
+        h->overflow = overflow ? 1 : 0;
         const uint32_t nz_bytes = static_cast<uint32_t>(end - base) * 4u;
         const uint32_t rp_bytes = rp_ok ? static_cast<uint32_t>(window_rows + 4) * 4u : 0u;
         dev::mbar_arrive_expect_tx(bars + s, 2u * nz_bytes + rp_bytes);
@@ -327,6 +376,11 @@ csr_pipe_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* 
         const int r0 = w * window_rows;
         const int nr = min(window_rows, rows - r0);
 
+        if (h.overflow) {  // CTA-uniform
+            // products in the stage's value area, running sums in its column area (window * LPR <= cap)
+            pipe_overflow_window<LPR>(nr, r0, rows_per_group, row_ptrs, col_indices, values, x, y, stage_rp(s),
+                                      h.rp_staged != 0, stage_val(s), reinterpret_cast<float*>(stage_col(s)), cap);
+        } else
         // U elements of a row are gathered per batch, so up to U independent x gathers are in
         // flight per thread (one gather latency for rows up to U*LPR long).
         for (int i = 0; i < rows_per_group; ++i) {
@@ -387,6 +441,7 @@ cudaError_t launch_pipe_lpr_u(const CsrView& A, const float* x, float* y, cudaSt
     rpg = rpg < 1 ? 1 : (rpg > 8 ? 8 : rpg);
     const int window = groups * rpg;
     int cap = static_cast<int>(1.125 * avg * window) + 32;  // windows that exceed it fetch the excess from global
+    if (cap < kThreads * rpg) cap = kThreads * rpg;  // the overflow path keeps window * LPR running sums there
     cap = (cap + 127) / 128 * 128;
     static const int env_stages = stream_env_int("SPMV_B200_CSR_STAGES", 0);
     static const int env_ctas = stream_env_int("SPMV_B200_CSR_CTAS_PER_SM", 0);
