@@ -29,6 +29,8 @@
 #include "internal.hpp"
 
 #include <algorithm>
+#include <mutex>
+#include <unordered_map>
 
 namespace spmv {
 namespace b200 {
@@ -219,7 +221,7 @@ cudaError_t launch_stream_lpr(const CsrView& A, const float* x, float* y, cudaSt
 }
 
 // ---------------------------------------------------------------------------
-// csr_pipe_kernel<LPR, U>: the persistent, TMA-staged form of the row-owner
+// csr_pipe_kernel<LPR, U, ROBUST>: the persistent, TMA-staged form of the row-owner
 // kernel (the default when the arrays are 16-byte aligned).
 //
 // The grid is a small multiple of the SM count; CTA b walks row windows b,
@@ -293,7 +295,12 @@ __device__ __noinline__ void pipe_overflow_window(int nr, int r0, int rows_per_g
     }
 }
 
-template <int LPR, int U>
+// ROBUST = true adds the cooperative overflow path (a few registers and ~5 % on regular
+// matrices); ROBUST = false stages what fits and lets row owners fetch the rest from global,
+// which is only acceptable when no row comes near the stage capacity.  The launcher picks by the
+// matrix's longest row (cached per device array, see longest_row_cached()); both are correct for
+// any input.
+template <int LPR, int U, bool ROBUST>
 __global__ void __launch_bounds__(kThreads)
 csr_pipe_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* __restrict__ col_indices,
                 const float* __restrict__ values, const float* __restrict__ x, float* __restrict__ y,
@@ -320,8 +327,9 @@ csr_pipe_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* 
         const int r0 = w * window_rows;
         const int base = n0 & ~3;
         int end = min((n1 + 3) & ~3, nnz & ~3);
-        const bool overflow = end - base > cap;  // does not fit a stage: nothing is staged, see pipe_overflow_window
+        const bool overflow = ROBUST && end - base > cap;  // does not fit a stage: nothing is staged
         if (overflow) end = base;
+        end = min(end, base + cap);
         end = max(end, base);
         const bool rp_ok = r0 + window_rows + 4 <= rows + 1;
         PipeStageHeader* h = stage_header(s);
@@ -376,7 +384,7 @@ csr_pipe_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* 
         const int r0 = w * window_rows;
         const int nr = min(window_rows, rows - r0);
 
-        if (h.overflow) {  // CTA-uniform
+        if (ROBUST && h.overflow) {  // CTA-uniform
             // products in the stage's value area, running sums in its column area (window * LPR <= cap)
             pipe_overflow_window<LPR>(nr, r0, rows_per_group, row_ptrs, col_indices, values, x, y, stage_rp(s),
                                       h.rp_staged != 0, stage_val(s), reinterpret_cast<float*>(stage_col(s)), cap);
@@ -430,32 +438,74 @@ int stream_env_int(const char* name, int fallback) {
     return v ? atoi(v) : fallback;
 }
 
-template <int LPR, int U>
-cudaError_t launch_pipe_lpr_u(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
+// window = groups * rows_per_group rows holding about 1.5 K non-zeros; cap = stage capacity
+template <int LPR>
+void pipe_geometry(const CsrView& A, int& rpg, int& cap) {
     constexpr int groups = kThreads / LPR;
     const double avg = static_cast<double>(A.nnz) / A.rows;
-    // window = groups * rows_per_group rows holding about 1.5 K non-zeros
-    int rpg = static_cast<int>(1536.0 / (avg * groups) + 0.5);
+    rpg = static_cast<int>(1536.0 / (avg * groups) + 0.5);
     static const int env_rpg = stream_env_int("SPMV_B200_CSR_RPG", 0);
     if (env_rpg > 0) rpg = env_rpg;
     rpg = rpg < 1 ? 1 : (rpg > 8 ? 8 : rpg);
     const int window = groups * rpg;
-    int cap = static_cast<int>(1.125 * avg * window) + 32;  // windows that exceed it fetch the excess from global
+    cap = static_cast<int>(1.125 * avg * window) + 32;
     if (cap < kThreads * rpg) cap = kThreads * rpg;  // the overflow path keeps window * LPR running sums there
     cap = (cap + 127) / 128 * 128;
+}
+
+// Longest row of a device CSR, computed once per (row_ptrs array, shape) with one pass over
+// row_ptrs and remembered.  It only steers the choice between two correct kernels, so a stale
+// entry (the array was rewritten in place) costs speed, never correctness.
+int longest_row_cached(const CsrView& A, cudaStream_t stream) {
+    static std::mutex mu;
+    static std::unordered_map<unsigned long long, int> cache;
+    const unsigned long long key = (reinterpret_cast<uintptr_t>(A.row_ptrs) * 0x9E3779B97F4A7C15ull) ^
+                                   (static_cast<unsigned long long>(A.rows) << 32) ^ static_cast<unsigned>(A.nnz);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) return it->second;
+    }
+    int* d_max = nullptr;
+    int longest = 0x7fffffff;  // unknown -> robust kernel
+    if (cudaMalloc(&d_max, sizeof(int)) == cudaSuccess) {
+        cudaMemsetAsync(d_max, 0, sizeof(int), stream);
+        if (launch_max_row_len(A, d_max, stream) == cudaSuccess &&
+            cudaMemcpyAsync(&longest, d_max, sizeof(int), cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+            cudaStreamSynchronize(stream) == cudaSuccess) {
+            std::lock_guard<std::mutex> lock(mu);
+            if (cache.size() > 4096) cache.clear();
+            cache[key] = longest;
+        } else {
+            cudaGetLastError();
+            longest = 0x7fffffff;
+        }
+        cudaFree(d_max);
+    } else {
+        cudaGetLastError();
+    }
+    return longest;
+}
+
+template <int LPR, int U, bool ROBUST>
+cudaError_t launch_pipe_lpr_u(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
+    constexpr int groups = kThreads / LPR;
+    int rpg, cap;
+    pipe_geometry<LPR>(A, rpg, cap);
+    const int window = groups * rpg;
     static const int env_stages = stream_env_int("SPMV_B200_CSR_STAGES", 0);
     static const int env_ctas = stream_env_int("SPMV_B200_CSR_CTAS_PER_SM", 0);
     const int stages = env_stages > 1 ? (env_stages > 16 ? 16 : env_stages) : 2;
     const size_t stage_bytes = sizeof(PipeStageHeader) + static_cast<size_t>(window + 4) * 4 + static_cast<size_t>(cap) * 8;
     const size_t smem = 128 + stages * stage_bytes;
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // caller falls back
-    cudaError_t e = cudaFuncSetAttribute(csr_pipe_kernel<LPR, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(csr_pipe_kernel<LPR, U, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     // A persistent grid must not exceed what is co-resident (registers AND shared memory),
     // otherwise the surplus CTAs only start when the first wave has finished.
     int fit = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, csr_pipe_kernel<LPR, U>, kThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, csr_pipe_kernel<LPR, U, ROBUST>, kThreads, smem);
     if (e != cudaSuccess) return e;
     if (fit < 1) return cudaErrorInvalidConfiguration;
     const int ctas_per_sm = (env_ctas > 0 && env_ctas < fit) ? env_ctas : fit;
@@ -465,7 +515,7 @@ cudaError_t launch_pipe_lpr_u(const CsrView& A, const float* x, float* y, cudaSt
     const int num_windows = (A.rows + window - 1) / window;
     int blocks = sms * ctas_per_sm;
     if (blocks > num_windows) blocks = num_windows;
-    csr_pipe_kernel<LPR, U><<<blocks, kThreads, smem, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values, x, y,
+    csr_pipe_kernel<LPR, U, ROBUST><<<blocks, kThreads, smem, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values, x, y,
                                                              window, rpg, cap, stages);
     count_launches(1);
     return cudaGetLastError();
@@ -478,9 +528,19 @@ cudaError_t launch_pipe_lpr(const CsrView& A, const float* x, float* y, cudaStre
     const double per_lane = static_cast<double>(A.nnz) / A.rows / LPR;
     int u = per_lane <= 4.0 ? 4 : (per_lane <= 6.0 ? 6 : 8);
     if (env_u > 0) u = env_u;
-    if (u <= 4) return launch_pipe_lpr_u<LPR, 4>(A, x, y, stream);
-    if (u <= 6) return launch_pipe_lpr_u<LPR, 6>(A, x, y, stream);
-    return launch_pipe_lpr_u<LPR, 8>(A, x, y, stream);
+    // a row that takes more than half a stage means windows that do not fit: robust variant
+    int rpg, cap;
+    pipe_geometry<LPR>(A, rpg, cap);
+    static const int env_robust = stream_env_int("SPMV_B200_CSR_ROBUST", -1);
+    const bool robust = env_robust >= 0 ? env_robust != 0 : longest_row_cached(A, stream) > cap / 2;
+    if (robust) {
+        if (u <= 4) return launch_pipe_lpr_u<LPR, 4, true>(A, x, y, stream);
+        if (u <= 6) return launch_pipe_lpr_u<LPR, 6, true>(A, x, y, stream);
+        return launch_pipe_lpr_u<LPR, 8, true>(A, x, y, stream);
+    }
+    if (u <= 4) return launch_pipe_lpr_u<LPR, 4, false>(A, x, y, stream);
+    if (u <= 6) return launch_pipe_lpr_u<LPR, 6, false>(A, x, y, stream);
+    return launch_pipe_lpr_u<LPR, 8, false>(A, x, y, stream);
 }
 
 bool pipe_eligible(const CsrView& A) {

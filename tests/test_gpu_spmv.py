@@ -310,9 +310,16 @@ def test_async_entry_points_and_launch_count(sp, orc, cuda):
             d_y = torch.full((rows,), float("nan"), device=cuda)
             before = sp.launch_count()
             assert sp.spmv_csr_async(A.mat, d_x, d_y, sp.make_config(k), stream.cuda_stream) == 0
-            assert sp.launch_count() - before == (3 if k == 2 else 1)
+            first = sp.launch_count() - before
+            # merge-path: partition + tile + fix-up; row-owner kernels: one launch, plus a one-off scan of
+            # the longest row the first time a row_ptrs array is seen (it picks the kernel variant)
+            assert first == 3 if k == 2 else first in (1, 2)
             stream.synchronize()
             assert_within_tolerance(d_y.cpu().numpy(), y64, scale, f"async {KERNELS[k]}")
+            before = sp.launch_count()
+            assert sp.spmv_csr_async(A.mat, d_x, d_y, sp.make_config(k), stream.cuda_stream) == 0
+            assert sp.launch_count() - before == (3 if k == 2 else 1)
+            stream.synchronize()
     A.close()
 
 
