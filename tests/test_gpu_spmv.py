@@ -351,3 +351,21 @@ def test_benchmark_harness_and_bandwidth(sp, cuda):
     assert m.achieved_bandwidth_gb_s > 0
     sp.ell_destroy(E)
     A.close()
+
+
+@pytest.mark.parametrize("env", [{"SPMV_B200_CSR_ROBUST": "0"}, {"SPMV_B200_CSR_ROBUST": "1"},
+                                 {"SPMV_B200_CSR_NO_PIPE": "1"}, {"SPMV_B200_MERGE_TMA": "1"},
+                                 {"SPMV_B200_ELL_VARIANT": "1"}, {"SPMV_B200_ELL_VARIANT": "3"}])
+def test_every_kernel_variant_forced(cuda, env):
+    """The launchers choose between kernel variants (fast / robust row-owner pipeline, register-staged
+    fall-backs, TMA-staged merge tiles, one-shot / register-staged ELL).  Each is forced here through
+    its tuning variable (read once per process, hence the subprocess) and must pass the same parity
+    tests: random shapes, outlier rows, unaligned pointers, the Laplacian."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_spmv.py"), "-q", "-x", "-m", "gpu",
+           "-k", "random_shapes or outlier_rows or unaligned or laplacian_medium or golden"]
+    p = subprocess.run(cmd, env={**os.environ, **env}, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout[-3000:]
