@@ -390,7 +390,61 @@ csr_pipe_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* 
                                       h.rp_staged != 0, stage_val(s), reinterpret_cast<float*>(stage_col(s)), cap);
         } else
         // U elements of a row are gathered per batch, so up to U independent x gathers are in
-        // flight per thread (one gather latency for rows up to U*LPR long).
+        // flight per thread (one gather latency for rows up to U*LPR long).  With several lanes
+        // per row (LPR > 1) two row slots of the group are walked together, otherwise the short
+        // per-lane share of a row would leave the lane with too few gathers in flight.
+        if (LPR > 1) {
+            for (int i = 0; i < rows_per_group; i += 2) {
+                const int rA = group + i * kGroups;
+                const int rB = group + (i + 1) * kGroups;
+                const bool okA = rA < nr, okB = (i + 1 < rows_per_group) && rB < nr;
+                int jA = 0, bA = 0, jB = 0, bB = 0;
+                if (okA) {
+                    jA = (h.rp_staged ? s_rp[rA] : __ldg(row_ptrs + r0 + rA)) + lane;
+                    bA = h.rp_staged ? s_rp[rA + 1] : __ldg(row_ptrs + r0 + rA + 1);
+                }
+                if (okB) {
+                    jB = (h.rp_staged ? s_rp[rB] : __ldg(row_ptrs + r0 + rB)) + lane;
+                    bB = h.rp_staged ? s_rp[rB + 1] : __ldg(row_ptrs + r0 + rB + 1);
+                }
+                float accA = 0.0f, accB = 0.0f;
+                while (jA < bA || jB < bB) {
+                    float vA[U], xA[U], vB[U], xB[U];
+                    int cA[U], cB[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int ja = jA + u * LPR, jb = jB + u * LPR;
+                        if (ja < bA) {
+                            if (ja < h.staged_end) { vA[u] = s_val[ja - h.base]; cA[u] = s_col[ja - h.base]; }
+                            else { vA[u] = dev::ld_stream_f(values + ja); cA[u] = dev::ld_stream_i(col_indices + ja); }
+                        }
+                        if (jb < bB) {
+                            if (jb < h.staged_end) { vB[u] = s_val[jb - h.base]; cB[u] = s_col[jb - h.base]; }
+                            else { vB[u] = dev::ld_stream_f(values + jb); cB[u] = dev::ld_stream_i(col_indices + jb); }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (jA + u * LPR < bA) xA[u] = dev::ld_x(x + cA[u]);
+                        if (jB + u * LPR < bB) xB[u] = dev::ld_x(x + cB[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (jA + u * LPR < bA) accA = __fadd_rn(accA, __fmul_rn(vA[u], xA[u]));
+                        if (jB + u * LPR < bB) accB = __fadd_rn(accB, __fmul_rn(vB[u], xB[u]));
+                    }
+                    jA += U * LPR;
+                    jB += U * LPR;
+                }
+#pragma unroll
+                for (int d = LPR / 2; d > 0; d >>= 1) {
+                    accA += __shfl_down_sync(0xffffffffu, accA, d, LPR);
+                    accB += __shfl_down_sync(0xffffffffu, accB, d, LPR);
+                }
+                if (lane == 0 && okA) y[r0 + rA] = accA;
+                if (lane == 0 && okB) y[r0 + rB] = accB;
+            }
+        } else
         for (int i = 0; i < rows_per_group; ++i) {
             const int r = group + i * kGroups;
             float acc = 0.0f;
@@ -443,7 +497,9 @@ template <int LPR>
 void pipe_geometry(const CsrView& A, int& rpg, int& cap) {
     constexpr int groups = kThreads / LPR;
     const double avg = static_cast<double>(A.nnz) / A.rows;
-    rpg = static_cast<int>(1536.0 / (avg * groups) + 0.5);
+    // measured on config 2 (profiles/r1_ell_tuning.md): ~1.5 K non-zeros per window for one lane per row,
+    // ~2.5 K when lanes share rows (two row slots are walked together there)
+    rpg = static_cast<int>((LPR == 1 ? 1536.0 : 2560.0) / (avg * groups) + 0.5);
     static const int env_rpg = stream_env_int("SPMV_B200_CSR_RPG", 0);
     if (env_rpg > 0) rpg = env_rpg;
     rpg = rpg < 1 ? 1 : (rpg > 8 ? 8 : rpg);
