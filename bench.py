@@ -203,7 +203,17 @@ def bench_kernel(torch, sp, stream, launch, bytes_per_launch, steps, warmup, dis
     return {"ms_per_step": per, "gbs": world * bytes_per_launch / (per * 1e-3) / 1e9}
 
 
-def build_rmat_shard(torch, gen, scale, edge_factor, seed, rank, world, device, chunk=1 << 24, row_weight=1):
+def relabel(v, scale):
+    """Bijective pseudo-random relabelling of vertex ids in [0, 2^scale) (xorshift, odd multiply,
+    xorshift), the role of Graph500's vertex permutation: it removes R-MAT's id/degree correlation."""
+    mask = (1 << scale) - 1
+    v = v ^ (v >> (scale // 2))
+    v = (v * 0x9E3779B1 + 0x7F4A7C15) & mask
+    return v ^ (v >> (scale // 2 + 1))
+
+
+def build_rmat_shard(torch, gen, scale, edge_factor, seed, rank, world, device, chunk=1 << 24, row_weight=1,
+                     relabelled=False):
     """This rank's row shard of the column-normalised R-MAT matrix without materialising the
     whole graph: pass 1 counts in/out degrees of every edge (bincount), pass 2 keeps the edges
     whose destination falls in this rank's nnz-balanced row range and sorts only those."""
@@ -223,6 +233,8 @@ def build_rmat_shard(torch, gen, scale, edge_factor, seed, rank, world, device, 
             u = gen.hash32(seed, e, stream=16 + level)
             s = (s << 1) | (u >= tb).to(torch.int64)
             d = (d << 1) | (((u >= ta) & (u < tb)) | (u >= tc)).to(torch.int64)
+        if relabelled:
+            s, d = relabel(s, scale), relabel(d, scale)
         return s, d
 
     for lo in range(0, n_edges, chunk):
@@ -393,13 +405,14 @@ def run_product_arm(args):
         torch.cuda.empty_cache()
 
     # ---- config 4 / 5: R-MAT SpMV (merge-path) and PageRank, row-sharded over the ranks -----------
-    def rmat_section(scale, seed, do_vector, do_pagerank):
-        log(f"R-MAT scale {scale}: build")
+    def rmat_section(scale, seed, do_vector, do_pagerank, relabelled=False):
+        log(f"R-MAT scale {scale}: build" + (" (relabelled vertices)" if relabelled else ""))
+        tag = "_relabelled" if relabelled else ""
         # SpMV shards balance the merge items (rows + nnz); PageRank shards also pay 4 bytes per
         # owned row to every peer, so rows weigh more there (tuned on 8 GPUs, profiles/)
-        weight = args.row_weight if args.row_weight >= 0 else (1 if not do_pagerank or world == 1 else 8)
+        weight = args.row_weight if args.row_weight >= 0 else (1 if not do_pagerank or world == 1 or relabelled else 8)
         n, bounds, srp, sci, sva, n_edges = build_rmat_shard(torch, gen, scale, 16, seed, rank, world, dev,
-                                                            row_weight=weight)
+                                                            row_weight=weight, relabelled=relabelled)
         torch.cuda.synchronize()
         shard = D.CudaShard(n, bounds[rank], srp, sci, sva, stream=s_ptr)
         xg = torch.full((n,), 1.0 / n, dtype=torch.float32, device=dev)
@@ -414,14 +427,14 @@ def run_product_arm(args):
             log(f"R-MAT scale {scale}: {name}")
             r = bench_kernel(torch, sp, stream, lambda: shard.spmv(xg, yg, kernel), 0, max(5, args.steps // 2), 3, dist_on)
             gbs = float(tot4.item()) / (r["ms_per_step"] * 1e-3) / 1e9
-            extra[f"rmat{scale}_{name}"] = {"gbs": gbs, "ms": r["ms_per_step"], "frac_of_measured_peak": gbs / world / peak,
+            extra[f"rmat{scale}{tag}_{name}"] = {"gbs": gbs, "ms": r["ms_per_step"], "frac_of_measured_peak": gbs / world / peak,
                                             "frac_of_8000": gbs / world / 8000.0, "bytes_all_ranks": float(tot4.item()),
                                             "nnz": n_edges, "rows": n, "scaling": "strong (one graph, row shards)"}
         if do_pagerank:
             # fixed number of iterations of the sharded loop (stop rule evaluated every iteration,
             # one iteration late), wall clock around the loop after a device sync, max over ranks
             shard.damping = 0.85
-            modes = ["p2p", "nccl"] if dist_on else ["single"]
+            modes = (["p2p"] if relabelled else ["p2p", "nccl"]) if dist_on else ["single"]
             with torch.cuda.stream(stream):
                 shard.setup_dangling()
             for mode in modes:
@@ -457,9 +470,10 @@ def run_product_arm(args):
                                    "+ NCCL all-reduce of 3 f64",
                             "nccl": "NCCL all-gather of the rank slices + all-reduce of 3 f64",
                             "single": "none (1 GPU)"}[mode]
-                extra["pagerank" if mode != "nccl" else "pagerank_nccl_allgather"] = {
+                extra[("pagerank" if mode != "nccl" else "pagerank_nccl_allgather") + tag] = {
                     "iters_per_s": iters / sec, "ms_per_iter": sec / iters * 1e3,
-                    "graph": f"R-MAT scale {scale} x16, d=0.85", "n": n, "nnz": n_edges, "iterations_timed": iters,
+                    "graph": f"R-MAT scale {scale} x16, d=0.85" + (", vertex ids relabelled (Graph500-style)" if relabelled
+                                                                   else ", no vertex permutation"), "n": n, "nnz": n_edges, "iterations_timed": iters,
                     "l2_residual_after": residual, "effective_gbs": it_bytes / (sec / iters) / 1e9, "scaling": "strong",
                     "frac_of_measured_peak": it_bytes / (sec / iters) / 1e9 / world / peak, "exchange": exchange,
                     "partition": f"work(row) = nnz + {weight}", "rows_per_rank_max": int(max(bounds[i + 1] - bounds[i] for i in range(world))),
@@ -476,6 +490,8 @@ def run_product_arm(args):
             rmat_section(args.pr_scale, 45, do_vector=False, do_pagerank=True)
     if args.only_pagerank:
         rmat_section(args.pr_scale, 45, do_vector=False, do_pagerank=True)
+    if args.relabelled and (not args.quick or args.only_pagerank):
+        rmat_section(args.pr_scale, 45, do_vector=False, do_pagerank=True, relabelled=True)
 
     if rank == 0:
         roofline = {"bound": "hbm", "achieved": launch_gbs, "peak": peak, "unit": "GB/s", "frac": launch_gbs / peak,
@@ -512,6 +528,8 @@ def main():
     ap.add_argument("--pr-iters", type=int, default=20)
     ap.add_argument("--row-weight", type=int, default=-1, help="partition work(row) = nnz + row_weight (-1: default policy)")
     ap.add_argument("--only-pagerank", action="store_true", help="tuning aid: headline + PageRank section only")
+    ap.add_argument("--relabelled", type=int, default=1,
+                    help="also run PageRank on the same R-MAT graph with relabelled vertex ids (extra.pagerank_relabelled)")
     ap.add_argument("--ncu-traffic", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture")
     args = ap.parse_args()
