@@ -12,7 +12,8 @@ algorithmic bytes (reference src/bandwidth.cpp:66-75) x steps / device time,
 inputs resident in HBM.  `e2e` is the same metric through the blocking
 reference-facing C-ABI call with HOST x / y buffers (H2D of x and D2H of y in
 the timed region).  `extra` carries the other BASELINE configurations
-(CSR kernels on config 2, config 3, config 4 R-MAT SpMV, PageRank iter/s).
+(CSR kernels on config 2, config 3, config 4 R-MAT SpMV -- plain merge-path and
+through a hub-column plan --, PageRank iter/s).
 
 N > 1 (one rank per GPU, NCCL): weak scaling for the headline -- every rank
 owns a 16.7 M-row band (row shard) of a 4096 x (4096 N) Laplacian with the
@@ -430,7 +431,33 @@ def run_product_arm(args):
             extra[f"rmat{scale}{tag}_{name}"] = {"gbs": gbs, "ms": r["ms_per_step"], "frac_of_measured_peak": gbs / world / peak,
                                             "frac_of_8000": gbs / world / 8000.0, "bytes_all_ranks": float(tot4.item()),
                                             "nnz": n_edges, "rows": n, "scaling": "strong (one graph, row shards)"}
+        # the same product through a CSR plan: merge coordinates computed once + hub-column table
+        # (csr_hot_kernels.cu); bit-identical results, checked here on the full-size shard
+        log(f"R-MAT scale {scale}: csr_merge through a hub-column plan")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        plan = sp.CsrPlan(shard.csr.ptr)
+        torch.cuda.synchronize()
+        plan_ms = (time.perf_counter() - t0) * 1e3
+        hot_columns, hot_nnz, hot_mode = plan.info()
+        y_slice = yg[bounds[rank]:bounds[rank] + rows_p]
+        y_ref = y_slice.clone()  # left by the plain merge-path run above (or the vector kernel)
+        shard.spmv(xg, yg, sp.MERGE_PATH)
+        torch.cuda.synchronize()
+        y_ref.copy_(y_slice)
+        r = bench_kernel(torch, sp, stream, lambda: plan.spmv(xg, y_slice, s_ptr), 0, max(5, args.steps // 2), 3, dist_on)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(y_ref.view(torch.int32), y_slice.view(torch.int32)))
+        gbs = float(tot4.item()) / (r["ms_per_step"] * 1e-3) / 1e9
+        extra[f"rmat{scale}{tag}_csr_merge_hub_plan"] = {
+            "gbs": gbs, "ms": r["ms_per_step"], "frac_of_measured_peak": gbs / world / peak, "frac_of_8000": gbs / world / 8000.0,
+            "bytes_all_ranks": float(tot4.item()), "hub_columns_rank0": hot_columns,
+            "hub_nnz_fraction_rank0": hot_nnz / max(sci.numel(), 1), "plan_mode": hot_mode, "plan_build_ms": plan_ms,
+            "bit_identical_to_csr_merge": same, "scaling": "strong (one graph, row shards)"}
+        plan.close()
+        del y_ref
         if do_pagerank:
+            hub_cols = shard.set_hot(-1)
             # fixed number of iterations of the sharded loop (stop rule evaluated every iteration,
             # one iteration late), wall clock around the loop after a device sync, max over ranks
             shard.damping = 0.85
@@ -476,7 +503,7 @@ def run_product_arm(args):
                                                                    else ", no vertex permutation"), "n": n, "nnz": n_edges, "iterations_timed": iters,
                     "l2_residual_after": residual, "effective_gbs": it_bytes / (sec / iters) / 1e9, "scaling": "strong",
                     "frac_of_measured_peak": it_bytes / (sec / iters) / 1e9 / world / peak, "exchange": exchange,
-                    "partition": f"work(row) = nnz + {weight}", "rows_per_rank_max": int(max(bounds[i + 1] - bounds[i] for i in range(world))),
+                    "hub_columns_rank0": hub_cols, "partition": f"work(row) = nnz + {weight}", "rows_per_rank_max": int(max(bounds[i + 1] - bounds[i] for i in range(world))),
                     "includes": "fused step + exchange + lagged host read of the residual every iteration; "
                                 "excluded: setup + final normalisation"}
                 del r_a, r_b

@@ -434,6 +434,48 @@ def launch_count():
     return int(lib.spmv_b200_launch_count())
 
 
+class CsrPlan:
+    """Merge coordinates + hub-column table of a device CSR (spmv_b200_csr_plan)."""
+
+    def __init__(self, A, max_hot_columns=0, force=False):
+        self.handle = C.c_void_p()
+        rc = lib.spmv_b200_csr_plan_create(A, int(max_hot_columns), int(bool(force)), C.byref(self.handle))
+        if rc != 0:
+            raise RuntimeError(f"csr_plan_create: {spmv_error_string(rc)}")
+        self._A = A  # the plan reads the matrix's device arrays
+
+    def info(self):
+        """(hot_columns, hot_nnz, mode); mode 0 plain tile kernel, 1 hub table, 2 all of x."""
+        n, z, m = C.c_int(0), C.c_longlong(0), C.c_int(0)
+        lib.spmv_b200_csr_plan_info(self.handle, C.byref(n), C.byref(z), C.byref(m))
+        return n.value, z.value, m.value
+
+    def spmv(self, d_x, d_y, stream=0):
+        return lib.spmv_b200_spmv_csr_planned(self.handle, dptr(d_x), dptr(d_y), C.c_void_p(stream))
+
+    def close(self):
+        if self.handle:
+            lib.spmv_b200_csr_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def csr_forget_plan(A):
+    lib.spmv_b200_csr_forget_plan(A)
+
+
+def csr_auto_plan_info(A):
+    """(hot_columns, hot_nnz) of the plan spmv_csr(MERGE_PATH) attached to A's upload, (0, 0) if none."""
+    n, z = C.c_int(0), C.c_longlong(0)
+    lib.spmv_b200_csr_auto_plan_info(A, C.byref(n), C.byref(z))
+    return n.value, z.value
+
+
 def merge_path_search(diagonal, row_ptrs, num_rows, nnz):
     _keep, p = _i32(row_ptrs)
     r, z = C.c_int(0), C.c_int(0)

@@ -352,6 +352,39 @@ int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, int parts, int* 
     return spmv_b200_partition_rows_weighted(row_ptrs, num_rows, parts, 0, bounds);
 }
 
+int spmv_b200_csr_plan_create(const spmv_b200_csr* A, int max_hot_columns, int force, spmv_b200_csr_plan** out) {
+    return guarded([&] {
+        return b200::csr_plan_create(cpp(A), max_hot_columns, force != 0, reinterpret_cast<b200::CsrPlan**>(out));
+    });
+}
+void spmv_b200_csr_plan_destroy(spmv_b200_csr_plan* plan) { b200::csr_plan_destroy(reinterpret_cast<b200::CsrPlan*>(plan)); }
+int spmv_b200_csr_plan_info(const spmv_b200_csr_plan* plan, int* hot_columns, long long* hot_nnz, int* mode) {
+    if (!plan) return kBadArg;
+    b200::csr_plan_info(reinterpret_cast<const b200::CsrPlan*>(plan), hot_columns, hot_nnz, mode);
+    return 0;
+}
+int spmv_b200_spmv_csr_planned(const spmv_b200_csr_plan* plan, const float* d_x, float* d_y, void* stream) {
+    return guarded([&] {
+        return b200::spmv_csr_planned(reinterpret_cast<const b200::CsrPlan*>(plan), d_x, d_y,
+                                      static_cast<cudaStream_t>(stream));
+    });
+}
+int spmv_b200_csr_auto_plan_info(const spmv_b200_csr* A, int* hot_columns, long long* hot_nnz) {
+    if (!A) return kBadArg;
+    b200::auto_plan_info(cpp(A), hot_columns, hot_nnz);
+    return 0;
+}
+void spmv_b200_csr_forget_plan(const spmv_b200_csr* A) {
+    if (A) b200::forget_device_csr(cpp(A)->d_col_indices);
+}
+
+int spmv_b200_pr_plan_set_hot(spmv_b200_pr_plan* plan, int max_hot_columns, int force, void* stream) {
+    return guarded([&] {
+        return b200::pr_plan_set_hot(reinterpret_cast<b200::PrPlan*>(plan), max_hot_columns, force != 0,
+                                     static_cast<cudaStream_t>(stream));
+    });
+}
+
 int spmv_b200_pr_plan_create(const spmv_b200_csr* shard, int row_offset, int n_global, void* stream,
                              spmv_b200_pr_plan** out) {
     return guarded([&] {

@@ -36,8 +36,7 @@
 // Roofline: HBM.  Algorithmic bytes per launch = 8*nnz + 4*(rows+1) + 4*cols +
 // 4*rows (reference src/bandwidth.cpp:34-42); merge-path timing includes
 // partition + tile + fix-up, as the reference's includes its memset.
-#include "device_utils.cuh"
-#include "internal.hpp"
+#include "merge_rows.cuh"
 
 #include <climits>
 
@@ -77,26 +76,6 @@ MergePlan merge_plan_carve(void* block, int rows, int nnz, bool with_partials) {
 
 namespace {
 
-constexpr int kT = kMergeThreads;
-constexpr int kIPT = kMergeItemsPerThread;
-constexpr int kTile = kMergeTile;
-
-// ---------------------------------------------------------------- level 1 ----
-// Canonical diagonal search: list A = row END offsets row_ptrs[1..rows], list
-// B = non-zero indices 0..nnz-1; A wins ties (a row ends before the non-zero
-// with the same index is consumed).
-__device__ __forceinline__ int2 diagonal_search_global(int diagonal, const int* __restrict__ row_ptrs,
-                                                       int rows, int nnz) {
-    int lo = max(diagonal - nnz, 0);
-    int hi = min(diagonal, rows);
-    while (lo < hi) {
-        const int mid = lo + ((hi - lo) >> 1);
-        if (__ldg(row_ptrs + mid + 1) <= diagonal - mid - 1) lo = mid + 1;
-        else hi = mid;
-    }
-    return make_int2(lo, diagonal - lo);
-}
-
 __global__ void merge_partition_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
                                        int num_tiles, int2* __restrict__ coords) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,75 +84,6 @@ __global__ void merge_partition_kernel(int rows, int nnz, const int* __restrict_
     const long long d = static_cast<long long>(t) * kTile;
     coords[t] = diagonal_search_global(static_cast<int>(d < total ? d : total), row_ptrs, rows, nnz);
 }
-
-// -------------------------------------------------------------- epilogues ----
-
-struct NoSums {
-    __device__ __forceinline__ void clear() {}
-};
-struct RankSums {
-    double l2, l1, dangling;
-    __device__ __forceinline__ void clear() { l2 = 0.0; l1 = 0.0; dangling = 0.0; }
-};
-
-// y[row] = sum
-struct PlainRow {
-    using Sums = NoSums;
-    static constexpr bool kReduces = false;
-    float* y;
-    __device__ __forceinline__ float prepare() const { return 0.0f; }
-    __device__ __forceinline__ void finish(int row, float sum, Sums&, float) const { y[row] = sum; }
-    __device__ __forceinline__ void park(int row, float partial) const { y[row] = partial; }
-    __device__ __forceinline__ float parked(int row) const { return y[row]; }
-    __device__ __forceinline__ void publish_rows(int, int, int) const {}
-    __device__ __forceinline__ void publish_row(int) const {}
-};
-
-// fused PageRank update of one finished row
-struct PageRankRow {
-    using Sums = RankSums;
-    static constexpr bool kReduces = true;
-    PageRankStepArgs a;
-    // d * dsum / n (reference src/pagerank.cu:111: damping * dangling_sum / n, left to right in fp32)
-    __device__ __forceinline__ float prepare() const {
-        return __fdiv_rn(__fmul_rn(a.damping, *a.d_dsum), static_cast<float>(a.n_global));
-    }
-    __device__ __forceinline__ void finish(int row, float sum, Sums& s, float dangling_term) const {
-        const int g = a.row_offset + row;
-        // reference src/pagerank.cu:113: (damping * y + dangling_contrib) + teleport
-        const float v = __fadd_rn(__fadd_rn(__fmul_rn(a.damping, sum), dangling_term), a.teleport);
-        a.r_new[g] = v;
-        const double diff = static_cast<double>(v) - static_cast<double>(a.r_old[g]);
-        s.l2 += diff * diff;
-        s.l1 += fabs(diff);
-        if ((a.bits[g >> 5] >> (g & 31)) & 1u) s.dangling += static_cast<double>(v);
-    }
-    __device__ __forceinline__ void park(int row, float partial) const { a.r_new[a.row_offset + row] = partial; }
-    __device__ __forceinline__ float parked(int row) const { return a.r_new[a.row_offset + row]; }
-    // Fused slice exchange (the "all-gather" of the sharded iteration): after a CTA-wide barrier
-    // the rows [row_lo, row_hi) this tile has just finished are copied from the local r_new
-    // (still in L2) into the r_new buffer of every peer GPU with coalesced stores over NVLink --
-    // one contiguous run per peer instead of one 4-byte packet per row.
-    __device__ __forceinline__ void publish_rows(int row_lo, int row_hi, int tid) const {
-        if (a.n_peers <= 1) return;
-        const int g0 = a.row_offset + row_lo, g1 = a.row_offset + row_hi;
-        const volatile float* src = a.r_new;
-#pragma unroll
-        for (int p = 0; p < kMaxPeers; ++p) {  // static indices: the pointer table stays in the constant bank
-            if (p >= a.n_peers || p == a.self_rank) continue;
-            float* dst = a.peers[p];
-            for (int g = g0 + tid; g < g1; g += kT) dst[g] = src[g];
-        }
-    }
-    __device__ __forceinline__ void publish_row(int row) const {  // a single row finished by the fix-up
-        if (a.n_peers <= 1) return;
-        const int g = a.row_offset + row;
-        const float v = a.r_new[g];
-#pragma unroll
-        for (int p = 0; p < kMaxPeers; ++p)
-            if (p < a.n_peers && p != a.self_rank) a.peers[p][g] = v;
-    }
-};
 
 // block-wide sum of RankSums into partials[slot*3 .. +3] (fixed order)
 __device__ __forceinline__ void block_store_sums(const RankSums& s, double* __restrict__ partials, int slot,
@@ -322,7 +232,7 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
                     first_sum = running;
                     first_row = r;
                 } else {
-                    row_op.finish(row_s + r, running, sums, row_ctx);
+                    row_op.tile_finish(row_s + r, running, sums, row_ctx);
                 }
                 running = 0.0f;
                 ++r;
@@ -365,7 +275,7 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
     if (emitted) {
         const float total = carry_in + first_sum;
         if (first_row == 0 && first_row_split) row_op.park(row_s, total);  // level 3 finishes it
-        else row_op.finish(row_s + first_row, total, sums, row_ctx);
+        else row_op.tile_finish(row_s + first_row, total, sums, row_ctx);
     }
 
     // ---- tile carry-out: the row still open at the tile end ------------------------
@@ -379,8 +289,8 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
     }
 
     if (Row::kReduces) {
-        __syncthreads();  // every finish() store of this CTA is visible CTA-wide
-        row_op.publish_rows(row_s + (first_row_split ? 1 : 0), c1.x, tid);
+        __syncthreads();  // every raw row sum of this CTA is visible CTA-wide
+        row_op.tile_epilogue(row_s + (first_row_split ? 1 : 0), c1.x, tid, sums, row_ctx);
         block_store_sums(sums, partials, tile, s_sums);
     }
 }
@@ -390,7 +300,7 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
 template <class Row>
 __global__ void __launch_bounds__(256)
 merge_fixup_kernel(int num_tiles, const int* __restrict__ carry_row, const float* __restrict__ carry_val,
-                   Row row_op, double* __restrict__ partials) {
+                   Row row_op, double* __restrict__ partials, int partial_base) {
     __shared__ double s_sums[256 / 32][3];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     typename Row::Sums sums;
@@ -406,7 +316,7 @@ merge_fixup_kernel(int num_tiles, const int* __restrict__ carry_row, const float
             row_op.publish_row(row);
         }
     }
-    if (Row::kReduces) block_store_sums(sums, partials, num_tiles + blockIdx.x, s_sums);
+    if (Row::kReduces) block_store_sums(sums, partials, partial_base + blockIdx.x, s_sums);
 }
 
 // final deterministic reduction of the per-CTA partial sums -> out[3]
@@ -451,7 +361,7 @@ cudaError_t run_tiles(const CsrView& A, const float* x, const MergePlan& plan, c
                                                                      x, plan.coords, plan.carry_row, plan.carry_val,
                                                                      row_op, plan.partials, use_tma);
     merge_fixup_kernel<Row><<<plan.fixup_blocks, 256, 0, stream>>>(plan.num_tiles, plan.carry_row, plan.carry_val,
-                                                                   row_op, plan.partials);
+                                                                   row_op, plan.partials, plan.num_tiles);
     count_launches(2);
     return cudaGetLastError();
 }
@@ -471,6 +381,28 @@ cudaError_t launch_merge_spmv(const CsrView& A, const float* x, float* y, const 
     if (A.rows <= 0) return cudaSuccess;
     PlainRow op{y};
     return run_tiles(A, x, plan, op, stream);
+}
+
+// Level 3 alone, for tile kernels that live elsewhere (csr_hot_kernels.cu).  The PageRank flavour
+// also folds the `partial_base` per-worker sums written by the tile kernel and its own per-CTA sums.
+cudaError_t launch_merge_fixup(const MergePlan& plan, float* y, cudaStream_t stream) {
+    if (plan.num_tiles <= 0) return cudaSuccess;
+    PlainRow op{y};
+    merge_fixup_kernel<PlainRow><<<plan.fixup_blocks, 256, 0, stream>>>(plan.num_tiles, plan.carry_row, plan.carry_val,
+                                                                        op, plan.partials, 0);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_fixup_pagerank(const MergePlan& plan, const PageRankStepArgs& args, int partial_base,
+                                        cudaStream_t stream) {
+    if (plan.num_tiles <= 0) return cudaSuccess;
+    PageRankRow op{args};
+    merge_fixup_kernel<PageRankRow><<<plan.fixup_blocks, 256, 0, stream>>>(plan.num_tiles, plan.carry_row,
+                                                                           plan.carry_val, op, plan.partials, partial_base);
+    reduce_partials_kernel<<<1, 1024, 0, stream>>>(plan.partials, partial_base + plan.fixup_blocks, args.out);
+    count_launches(2);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_merge_pagerank(const CsrView& A, const MergePlan& plan, const PageRankStepArgs& args,

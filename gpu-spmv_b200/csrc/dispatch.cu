@@ -18,7 +18,9 @@
 #include "internal.hpp"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
+#include <new>
 #include <unordered_map>
 
 namespace spmv {
@@ -52,7 +54,7 @@ void* Scratch::reserve(size_t bytes) {
 }
 
 cudaError_t dispatch_csr(const CsrView& A, const float* x, float* y, int kernel_type, Scratch& scratch,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const HotPlan* hot) {
     if (A.rows <= 0) return cudaSuccess;
     switch (kernel_type) {
         case SpMVConfig::MERGE_PATH: {
@@ -62,6 +64,8 @@ cudaError_t dispatch_csr(const CsrView& A, const float* x, float* y, int kernel_
             const MergePlan plan = merge_plan_carve(block, A.rows, A.nnz, false);
             cudaError_t e = launch_merge_partition(A, plan, stream);
             if (e != cudaSuccess) return e;
+            if (hot && (hot->n_hot > 0) && hot->nnz == A.nnz && hot->cols == A.cols)
+                return launch_hot_spmv(A, *hot, x, y, plan, stream);
             return launch_merge_spmv(A, x, y, plan, stream);
         }
         case SpMVConfig::VECTOR_CSR:
@@ -70,6 +74,147 @@ cudaError_t dispatch_csr(const CsrView& A, const float* x, float* y, int kernel_
         default:
             return launch_csr_stream(A, x, y, 1, stream);
     }
+}
+
+// ---- column plans ---------------------------------------------------------------------
+// Explicit plan (additive API): merge coordinates computed once + the hub-column plan.
+struct CsrPlan {
+    CsrView A{};
+    HotPlan hot;
+    Scratch merge_block;
+    MergePlan merge;
+};
+
+int csr_plan_create(const CSRMatrix* A, int max_hot_columns, bool force, CsrPlan** out) {
+    if (!A || !out) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
+    if (!A->d_row_ptrs || !A->d_col_indices || (A->nnz > 0 && !A->d_values))
+        return static_cast<int>(SpMVError::INVALID_FORMAT);
+    CsrPlan* p = new (std::nothrow) CsrPlan();
+    if (!p) return static_cast<int>(SpMVError::OUT_OF_MEMORY);
+    p->A = view_of(A);
+    cudaStream_t stream = nullptr;
+    if (p->A.rows > 0 && p->A.nnz > 0) {
+        void* block = p->merge_block.reserve(merge_plan_bytes(p->A.rows, p->A.nnz, false));
+        if (!block) {
+            delete p;
+            return static_cast<int>(SpMVError::CUDA_MALLOC);
+        }
+        p->merge = merge_plan_carve(block, p->A.rows, p->A.nnz, false);
+        cudaError_t e = launch_merge_partition(p->A, p->merge, stream);
+        if (e == cudaSuccess) e = hot_plan_build(p->A, &p->hot, max_hot_columns, force, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            hot_plan_release(&p->hot);
+            delete p;
+            return static_cast<int>(e == cudaErrorMemoryAllocation ? SpMVError::CUDA_MALLOC : SpMVError::KERNEL_LAUNCH);
+        }
+    }
+    *out = p;
+    return 0;
+}
+
+void csr_plan_destroy(CsrPlan* p) {
+    if (!p) return;
+    hot_plan_release(&p->hot);
+    delete p;
+}
+
+void csr_plan_info(const CsrPlan* p, int* hot_columns, long long* hot_nnz, int* mode) {
+    if (hot_columns) *hot_columns = p ? p->hot.n_hot : 0;
+    if (hot_nnz) *hot_nnz = p ? p->hot.hot_nnz : 0;
+    if (mode) *mode = !p || p->hot.n_hot <= 0 ? 0 : (p->hot.all_hot ? 2 : 1);
+}
+
+int spmv_csr_planned(const CsrPlan* p, const float* d_x, float* d_y, cudaStream_t stream) {
+    if (!p || !d_x || !d_y) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
+    const CsrView& A = p->A;
+    if (A.rows <= 0) return 0;
+    cudaError_t e;
+    if (A.nnz <= 0) e = launch_csr_stream(A, d_x, d_y, 1, stream);  // writes zeros
+    else if (p->hot.n_hot > 0) e = launch_hot_spmv(A, p->hot, d_x, d_y, p->merge, stream);
+    else e = launch_merge_spmv(A, d_x, d_y, p->merge, stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return static_cast<int>(SpMVError::KERNEL_LAUNCH);
+    }
+    return 0;
+}
+
+// Automatic plans for spmv_csr(MERGE_PATH): only for device arrays uploaded by csr_to_gpu (the
+// library allocated them and sees them freed), built on the second merge-path call over the same
+// arrays.  Only col_indices is re-encoded; values and x are read live.  A caller that overwrites
+// d_col_indices of such an upload IN PLACE must call spmv_b200_csr_forget_plan.
+namespace {
+struct AutoEntry {
+    int rows = 0, nnz = 0;
+    int calls = 0;
+    bool tried = false;
+    HotPlan hot;
+};
+std::mutex g_auto_mu;
+std::unordered_map<const void*, AutoEntry*> g_auto;
+
+int hot_env_mode() {
+    static const int mode = [] {
+        const char* v = getenv("SPMV_B200_HOT");
+        return v ? atoi(v) : -1;
+    }();
+    return mode;
+}
+}  // namespace
+
+void note_device_csr(const CSRMatrix* A) {
+    if (!A || !A->d_col_indices || hot_env_mode() == 0) return;
+    std::lock_guard<std::mutex> lock(g_auto_mu);
+    AutoEntry*& e = g_auto[A->d_col_indices];
+    if (e) {
+        hot_plan_release(&e->hot);
+        delete e;
+    }
+    e = new AutoEntry();
+    e->rows = A->num_rows;
+    e->nnz = A->nnz;
+}
+
+void forget_device_csr(const void* d_col_indices) {
+    if (!d_col_indices) return;
+    std::lock_guard<std::mutex> lock(g_auto_mu);
+    auto it = g_auto.find(d_col_indices);
+    if (it == g_auto.end()) return;
+    hot_plan_release(&it->second->hot);
+    delete it->second;
+    g_auto.erase(it);
+}
+
+// state of the automatic plan attached to A's device arrays (0 columns: none)
+void auto_plan_info(const CSRMatrix* A, int* hot_columns, long long* hot_nnz) {
+    if (hot_columns) *hot_columns = 0;
+    if (hot_nnz) *hot_nnz = 0;
+    if (!A || !A->d_col_indices) return;
+    std::lock_guard<std::mutex> lock(g_auto_mu);
+    auto it = g_auto.find(A->d_col_indices);
+    if (it == g_auto.end()) return;
+    if (hot_columns) *hot_columns = it->second->hot.n_hot;
+    if (hot_nnz) *hot_nnz = it->second->hot.hot_nnz;
+}
+
+// nullptr: no plan (not an upload of ours, first call, or not worthwhile)
+static const HotPlan* auto_hot_plan(const CSRMatrix* A, cudaStream_t stream) {
+    if (hot_env_mode() == 0 || !A->d_col_indices) return nullptr;
+    std::lock_guard<std::mutex> lock(g_auto_mu);
+    auto it = g_auto.find(A->d_col_indices);
+    if (it == g_auto.end()) return nullptr;
+    AutoEntry* e = it->second;
+    if (e->rows != A->num_rows || e->nnz != A->nnz) return nullptr;  // the struct was edited by hand
+    if (!e->tried && e->calls++ >= 1) {
+        e->tried = true;
+        if (hot_plan_build(view_of(A), &e->hot, 0, hot_env_mode() > 0, stream) != cudaSuccess) {
+            cudaGetLastError();
+            hot_plan_release(&e->hot);
+        }
+    }
+    return e->hot.n_hot > 0 ? &e->hot : nullptr;
 }
 
 namespace {
@@ -165,8 +310,10 @@ SpMVResult spmv_csr(const CSRMatrix* A, const float* d_x, float* d_y, const SpMV
     if (!ctx) return b200::failed(SpMVError::KERNEL_LAUNCH);  // no usable device: fail, never compute on the host
 
     cudaStream_t stream = nullptr;  // legacy default stream, as the reference
+    const b200::HotPlan* hot =
+        kernel == static_cast<int>(SpMVConfig::MERGE_PATH) ? b200::auto_hot_plan(A, stream) : nullptr;
     cudaEventRecord(ctx->start, stream);
-    cudaError_t e = b200::dispatch_csr(b200::view_of(A), d_x, d_y, kernel, ctx->scratch, stream);
+    cudaError_t e = b200::dispatch_csr(b200::view_of(A), d_x, d_y, kernel, ctx->scratch, stream, hot);
     cudaEventRecord(ctx->stop, stream);
     cudaError_t sync = cudaEventSynchronize(ctx->stop);
     cudaError_t last = cudaGetLastError();

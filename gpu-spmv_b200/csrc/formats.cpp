@@ -5,7 +5,7 @@
 // Pure integer / copy logic; results are bit-identical to the reference
 // (src/csr_matrix.cpp, src/ell_matrix.cpp) -- tests/test_formats_parity.py
 // checks that against the oracle and against oracle/_ref.
-#include "spmv_b200/api.hpp"
+#include "internal.hpp"
 
 #include <algorithm>
 #include <climits>
@@ -170,6 +170,7 @@ int csr_to_gpu(CSRMatrix* m) {
     }
     CUDA_CHECK(cudaMemcpy(m->d_row_ptrs, m->row_ptrs, nptr * sizeof(int), cudaMemcpyHostToDevice));
     m->owns_device_memory = true;
+    b200::note_device_csr(m);  // spmv_csr(MERGE_PATH) may attach a column plan to this upload
     return kOk;
 }
 
@@ -189,6 +190,7 @@ int csr_from_gpu(CSRMatrix* m) {
 // reference: src/csr_matrix.cpp:185-200
 void csr_free_gpu(CSRMatrix* m) {
     if (!m) return;
+    b200::forget_device_csr(m->d_col_indices);
     if (m->d_values) cudaFree(m->d_values);
     if (m->d_col_indices) cudaFree(m->d_col_indices);
     if (m->d_row_ptrs) cudaFree(m->d_row_ptrs);

@@ -57,7 +57,14 @@ private:
 
 // ---- merge-path geometry (shared by host planning and the kernels) ---------------
 constexpr int kMergeThreads = 256;
-constexpr int kMergeItemsPerThread = 8;
+// An ODD number of items per thread: thread t consumes products t*IPT .. t*IPT+IPT-1 from shared
+// memory, and an even stride puts 4 (stride 8: 8) lanes of a warp on the same bank.  ncu on R-MAT 24
+// with 8 items: half of the kernel's shared-memory wavefronts were bank-conflict replays, on the
+// same L1 data pipe that serves the x gathers (profiles/r1_hub_kernel.md).
+#ifndef SPMV_B200_MERGE_IPT
+#define SPMV_B200_MERGE_IPT 7
+#endif
+constexpr int kMergeItemsPerThread = SPMV_B200_MERGE_IPT;
 constexpr int kMergeTile = kMergeThreads * kMergeItemsPerThread;  // merge items per CTA
 
 struct MergePlan {
@@ -119,6 +126,33 @@ cudaError_t launch_merge_spmv(const CsrView& A, const float* x, float* y, const 
 cudaError_t launch_merge_pagerank(const CsrView& A, const MergePlan& plan,
                                   const PageRankStepArgs& args, cudaStream_t stream);
 
+// Level 3 alone (used by the tile kernel of csr_hot_kernels.cu)
+cudaError_t launch_merge_fixup(const MergePlan& plan, float* y, cudaStream_t stream);
+cudaError_t launch_merge_fixup_pagerank(const MergePlan& plan, const PageRankStepArgs& args, int partial_base,
+                                        cudaStream_t stream);
+
+// ---- hub-column plan (csr_hot_kernels.cu): x of the most referenced columns in shared memory ----
+struct HotPlan {
+    int n_hot = 0;            // columns kept in the shared-memory table (0: plan not worthwhile)
+    bool all_hot = false;     // every column fits: no re-encoding, the table is x itself
+    int* enc = nullptr;       // device [nnz]: col_indices with hub columns replaced by ~slot (owned)
+    int* hot_cols = nullptr;  // device [n_hot]: the column of every slot (owned)
+    long long hot_nnz = 0;    // non-zeros whose gather is served by the table
+    int nnz = 0;
+    int cols = 0;
+};
+int hot_capacity();                   // table slots that fit next to the tile buffers on this device
+int hot_default_capacity();           // table slots used when the caller does not say (tuned, < maximum)
+bool hot_worthwhile(const CsrView& A);  // large enough for the persistent grid
+// Builds the plan (synchronises `stream`).  capacity <= 0: the device maximum.  Success with
+// n_hot == 0 means "use the plain tile kernel".  force skips the size / benefit thresholds (tests).
+cudaError_t hot_plan_build(const CsrView& A, HotPlan* plan, int capacity, bool force, cudaStream_t stream);
+void hot_plan_release(HotPlan* plan);
+cudaError_t launch_hot_spmv(const CsrView& A, const HotPlan& hot, const float* x, float* y, const MergePlan& plan,
+                            cudaStream_t stream);
+cudaError_t launch_hot_pagerank(const CsrView& A, const HotPlan& hot, const MergePlan& plan,
+                                const PageRankStepArgs& args, cudaStream_t stream);
+
 // PageRank helpers
 cudaError_t launch_colsum(const CsrView& A, float* d_colsum, cudaStream_t stream);
 cudaError_t launch_dangling_bits(const float* d_colsum, int n, int valid_cols, uint32_t* d_bits,
@@ -136,7 +170,18 @@ cudaError_t launch_max_row_len(const CsrView& A, int* d_out, cudaStream_t stream
 // Chooses and launches the kernel(s) for `kernel_type` (any unknown value ->
 // SCALAR, as src/spmv_kernels.cu:287-288).  `scratch` backs merge-path plans.
 cudaError_t dispatch_csr(const CsrView& A, const float* x, float* y, int kernel_type,
-                         Scratch& scratch, cudaStream_t stream);
+                         Scratch& scratch, cudaStream_t stream, const HotPlan* hot = nullptr);
+
+// ---- explicit CSR plans (dispatch.cu): merge coordinates + hub-column plan, built once ------
+struct CsrPlan;
+int csr_plan_create(const CSRMatrix* A, int max_hot_columns, bool force, CsrPlan** out);
+void csr_plan_destroy(CsrPlan* plan);
+void csr_plan_info(const CsrPlan* plan, int* hot_columns, long long* hot_nnz, int* mode);
+int spmv_csr_planned(const CsrPlan* plan, const float* d_x, float* d_y, cudaStream_t stream);
+// automatic plans of spmv_csr(MERGE_PATH) follow the device arrays uploaded by csr_to_gpu
+void note_device_csr(const CSRMatrix* A);
+void forget_device_csr(const void* d_col_indices);
+void auto_plan_info(const CSRMatrix* A, int* hot_columns, long long* hot_nnz);
 
 // stream-ordered twins of spmv_csr / spmv_ell (no sync, no timing); return a SpMVError
 int spmv_csr_async(const CSRMatrix* A, const float* d_x, float* d_y, const SpMVConfig* config,
@@ -147,6 +192,7 @@ int spmv_ell_async(const ELLMatrix* A, const float* d_x, float* d_y, cudaStream_
 struct PrPlan;
 int pr_plan_create(const CSRMatrix* shard, int row_offset, int n_global, cudaStream_t stream, PrPlan** out);
 void pr_plan_destroy(PrPlan* plan);
+int pr_plan_set_hot(PrPlan* plan, int max_hot_columns, bool force, cudaStream_t stream);
 int pr_step(PrPlan* plan, const float* d_r_old, float* d_r_new, float damping, const float* d_dsum,
             const uint32_t* d_bits, double* d_partial, cudaStream_t stream,
             float* const* peer_r_new = nullptr, int n_peers = 0, int self_rank = 0);

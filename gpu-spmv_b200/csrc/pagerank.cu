@@ -21,6 +21,7 @@
 #include "internal.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 namespace spmv {
@@ -38,7 +39,17 @@ struct PrPlan {
     MergePlan merge;
     Scratch tmp_block;   // kTmpDoubles doubles
     double* tmp = nullptr;
+    HotPlan hot;         // hub columns of the shard (csr_hot_kernels.cu); n_hot == 0: plain tile kernel
+    ~PrPlan() { hot_plan_release(&hot); }
 };
+
+static int pr_hot_env() {
+    static const int mode = [] {
+        const char* v = getenv("SPMV_B200_HOT");
+        return v ? atoi(v) : -1;
+    }();
+    return mode;
+}
 
 int pr_plan_create(const CSRMatrix* shard, int row_offset, int n_global, cudaStream_t stream, PrPlan** out) {
     if (!shard || !out || row_offset < 0 || n_global < 0) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
@@ -63,11 +74,31 @@ int pr_plan_create(const CSRMatrix* shard, int row_offset, int n_global, cudaStr
         delete p;
         return static_cast<int>(SpMVError::KERNEL_LAUNCH);
     }
+    // the matrix is constant over the iterations: the hub-column plan pays for itself after a few
+    if (pr_hot_env() != 0 && hot_plan_build(p->A, &p->hot, 0, pr_hot_env() > 0, stream) != cudaSuccess) {
+        cudaGetLastError();
+        hot_plan_release(&p->hot);  // not fatal: the plain tile kernel is used
+    }
     *out = p;
     return 0;
 }
 
 void pr_plan_destroy(PrPlan* p) { delete p; }
+
+// max_hot_columns: 0 drops the plan (plain tile kernel), < 0 device maximum; force skips the
+// size / benefit thresholds.  Returns the number of hub columns now in use, or a negative error.
+int pr_plan_set_hot(PrPlan* p, int max_hot_columns, bool force, cudaStream_t stream) {
+    if (!p) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
+    cudaStreamSynchronize(stream);
+    hot_plan_release(&p->hot);
+    if (max_hot_columns == 0) return 0;
+    if (hot_plan_build(p->A, &p->hot, max_hot_columns < 0 ? 0 : max_hot_columns, force, stream) != cudaSuccess) {
+        cudaGetLastError();
+        hot_plan_release(&p->hot);
+        return static_cast<int>(SpMVError::CUDA_MALLOC);
+    }
+    return p->hot.n_hot;
+}
 
 int pr_step(PrPlan* p, const float* d_r_old, float* d_r_new, float damping, const float* d_dsum,
             const uint32_t* d_bits, double* d_partial, cudaStream_t stream, float* const* peer_r_new, int n_peers,
@@ -89,7 +120,9 @@ int pr_step(PrPlan* p, const float* d_r_old, float* d_r_new, float damping, cons
     a.d_dsum = d_dsum;
     a.bits = d_bits;
     a.out = d_partial;
-    if (launch_merge_pagerank(p->A, p->merge, a, stream) != cudaSuccess) {
+    const cudaError_t e = p->hot.n_hot > 0 ? launch_hot_pagerank(p->A, p->hot, p->merge, a, stream)
+                                           : launch_merge_pagerank(p->A, p->merge, a, stream);
+    if (e != cudaSuccess) {
         cudaGetLastError();
         return static_cast<int>(SpMVError::KERNEL_LAUNCH);
     }

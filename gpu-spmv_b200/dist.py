@@ -191,6 +191,14 @@ class CudaShard:
             sp.lib.spmv_b200_pr_plan_destroy(self.plan)
             self.plan = None
 
+    def set_hot(self, max_hot_columns=-1, force=False):
+        """Rebuilds the shard's hub-column table (csr_hot_kernels.cu): 0 = none, < 0 = device
+        maximum.  Returns the number of hub columns in use."""
+        n = sp.lib.spmv_b200_pr_plan_set_hot(self.plan, int(max_hot_columns), int(bool(force)), self._s())
+        if n < 0:
+            raise RuntimeError(f"pr_plan_set_hot: {sp.spmv_error_string(n)}")
+        return n
+
     def setup_dangling(self, group=None):
         """Dangling columns = global column sums equal to 0 (src/pagerank.cu:20-48)."""
         colsum = torch.zeros(self.n, dtype=torch.float32, device=self.dev)

@@ -279,6 +279,39 @@ SPMV_B200_API int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, in
 SPMV_B200_API int spmv_b200_partition_rows_weighted(const int* row_ptrs, int num_rows, int parts,
                                                     int row_weight, int* bounds /* [parts+1] */);
 
+/* ---- CSR plans: merge coordinates + hub-column table, built once --------- */
+
+/*
+ * Opaque plan over the DEVICE arrays of a CSR matrix for repeated MERGE_PATH products with the
+ * same sparsity pattern (the "persistent workspace" the reference lacks: its spmv_csr recomputes
+ * everything per call, src/spmv_kernels.cu:258-297).  It holds (1) the merge-path tile
+ * coordinates and (2), for scale-free matrices, the hub-column plan of csr_hot_kernels.cu: the x
+ * entries of the max_hot_columns most referenced columns are kept in shared memory by the kernel,
+ * and a PRIVATE re-encoding of col_indices tells it which.  The caller's arrays are not modified;
+ * d_values is read live at every product, d_row_ptrs / d_col_indices must not change while the
+ * plan is alive.  max_hot_columns <= 0: as many as fit next to the tile buffers (49152 on B200).
+ * force != 0 skips the size / benefit thresholds (tests).
+ */
+typedef struct spmv_b200_csr_plan spmv_b200_csr_plan;
+SPMV_B200_API int spmv_b200_csr_plan_create(const spmv_b200_csr* A, int max_hot_columns, int force,
+                                            spmv_b200_csr_plan** out);
+SPMV_B200_API void spmv_b200_csr_plan_destroy(spmv_b200_csr_plan* plan);
+/* hot_columns: table entries in use; hot_nnz: non-zeros served by the table;
+ * mode: 0 plain tile kernel, 1 hub-column table, 2 the whole x fits the table */
+SPMV_B200_API int spmv_b200_csr_plan_info(const spmv_b200_csr_plan* plan, int* hot_columns,
+                                          long long* hot_nnz, int* mode);
+/* y = A x through the plan; stream-ordered (stream is a cudaStream_t), no sync, no timing.
+ * Bit-identical to spmv_csr(MERGE_PATH). */
+SPMV_B200_API int spmv_b200_spmv_csr_planned(const spmv_b200_csr_plan* plan, const float* d_x,
+                                             float* d_y, void* stream);
+/* spmv_csr(MERGE_PATH) attaches such a plan by itself to device arrays uploaded by csr_to_gpu
+ * (second call onwards; SPMV_B200_HOT=0 disables).  After overwriting d_col_indices of such an
+ * upload IN PLACE, drop the stale plan with this call (csr_to_gpu / csr_free_gpu do it). */
+SPMV_B200_API void spmv_b200_csr_forget_plan(const spmv_b200_csr* A);
+/* the automatic plan currently attached to A's device arrays (hot_columns == 0: none) */
+SPMV_B200_API int spmv_b200_csr_auto_plan_info(const spmv_b200_csr* A, int* hot_columns,
+                                               long long* hot_nnz);
+
 /* ---- device-resident PageRank building blocks --------------------------- */
 
 /* Opaque plan over ONE row shard of an n_global x n_global column-normalised
@@ -289,6 +322,11 @@ typedef struct spmv_b200_pr_plan spmv_b200_pr_plan;
 SPMV_B200_API int spmv_b200_pr_plan_create(const spmv_b200_csr* shard, int row_offset,
                                            int n_global, void* stream, spmv_b200_pr_plan** out);
 SPMV_B200_API void spmv_b200_pr_plan_destroy(spmv_b200_pr_plan* plan);
+/* The plan carries the hub-column table of its shard when that pays (see spmv_b200_csr_plan).
+ * This call rebuilds it: max_hot_columns 0 = none (plain tile kernel), < 0 = device maximum.
+ * Returns the number of hub columns now in use (>= 0) or a negative status. */
+SPMV_B200_API int spmv_b200_pr_plan_set_hot(spmv_b200_pr_plan* plan, int max_hot_columns, int force,
+                                            void* stream);
 
 /* d_colsum[c] += sum of this shard's values in column c (fp32 atomics) */
 SPMV_B200_API int spmv_b200_pr_colsum(const spmv_b200_pr_plan* plan, float* d_colsum, void* stream);

@@ -2,7 +2,7 @@
 
     python scripts/profile_target.py <target> [launches]
     targets: ell_c2 vector_c2 scalar_c2 merge_c2 scalar_c3 merge_c3 merge_rmat<scale> vector_rmat<scale>
-             pagerank_rmat<scale>
+             pagerank_rmat<scale> hot<cap>_rmat<scale> (hub-column plan with <cap> table entries, 0 = max)
 Prints the CUDA-event time per launch (never a bench value when run under a profiler).
 """
 import ctypes as C
@@ -47,6 +47,10 @@ if what == "ell":
     assert sp.ell_from_csr_device(E, A.ptr) == 0
     nbytes = sp.ell_bytes(n, n, E.contents.max_nnz_per_row)
     run = lambda: sp.lib.spmv_b200_spmv_ell_async(E, sp.dptr(x), sp.dptr(y), None)  # noqa: E731
+elif what.startswith("hot"):
+    plan = sp.CsrPlan(A.ptr, int(what[3:] or 0))
+    print("plan (hot columns, hot nnz, mode):", plan.info())
+    run = lambda: plan.spmv(x, y)  # noqa: E731
 elif what == "pagerank":
     shard = D.CudaShard(n, 0, rp, ci, va)
     shard.setup_dangling()

@@ -1,0 +1,188 @@
+"""Hub-column plans (csr_hot_kernels.cu): the persistent merge-path kernel that keeps the x
+entries of the most referenced columns in shared memory.
+
+The plan only changes WHERE x[col] is read from, and the tiles, the per-thread order and the carry
+fix-up are those of the plain merge-path kernel, so every result must be BIT-IDENTICAL to
+spmv_csr(MERGE_PATH) without a plan -- and within the north_star tolerance of the oracle
+(|y - y_ref| <= 1e-5 * sum_j |a_ij x_j| per row against the f64-accumulating restatement of
+spmv_cpu_csr, reference src/spmv_cpu.cpp:6-16)."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_helpers import assert_within_tolerance, bits
+
+pytestmark = pytest.mark.gpu
+MERGE = 2
+
+
+def gen_mod():
+    import gpu_spmv_b200.gen as gen
+    return gen
+
+
+def plain_merge(sp, A, d_x, rows, cols):
+    d_y = torch.full((max(rows, 1),), float("nan"), dtype=torch.float32, device=d_x.device)
+    res = sp.spmv_csr(A.ptr, d_x, d_y, sp.make_config(MERGE), cols)
+    assert res.error_code == 0
+    return d_y[:rows].cpu().numpy()
+
+
+def check_plan(sp, orc, dev, rows, cols, rp, ci, va, x, caps, what, expect_mode=None):
+    rp, ci, va, x = (np.ascontiguousarray(rp, np.int32), np.ascontiguousarray(ci, np.int32),
+                     np.ascontiguousarray(va, np.float32), np.ascontiguousarray(x, np.float32))
+    y64, scale = orc.spmv_csr_f64(rows, rp, ci, va, x)
+    t = lambda a: torch.as_tensor(a).to(dev)  # noqa: E731
+    A = sp.DeviceCSR(rows, cols, t(rp), t(ci), t(va))
+    d_x = t(x)
+    y_plain = plain_merge(sp, A, d_x, rows, cols)
+    assert_within_tolerance(y_plain, y64, scale, f"{what} plain")
+    for cap in caps:
+        plan = sp.CsrPlan(A.ptr, cap, force=True)
+        n_hot, hot_nnz, mode = plan.info()
+        if expect_mode is not None:
+            assert mode == expect_mode, (what, cap, n_hot, mode)
+        if mode == 1:
+            assert 0 < n_hot <= (cap if cap > 0 else 1 << 20) and 0 < hot_nnz <= len(ci)
+            # the admitted columns are the most referenced ones
+            counts = np.bincount(ci, minlength=cols)
+            order = np.sort(counts)[::-1]
+            assert hot_nnz == int(order[:n_hot].sum()), (what, cap, n_hot)
+        d_y = torch.full((rows,), float("nan"), dtype=torch.float32, device=dev)
+        for _ in range(2):  # the plan is reusable
+            assert plan.spmv(d_x, d_y) == 0
+        torch.cuda.synchronize()
+        y = d_y.cpu().numpy()
+        assert_within_tolerance(y, y64, scale, f"{what} cap {cap}")
+        assert np.array_equal(bits(y), bits(y_plain)), f"{what} cap {cap}: differs from plain MERGE_PATH"
+        plan.close()
+
+
+@pytest.mark.parametrize("scale,ef,seed", [(12, 8, 2), (15, 16, 3), (17, 16, 4)])
+def test_rmat_hub_table_matches_plain_merge_path(sp, orc, cuda, scale, ef, seed):
+    gen = gen_mod()
+    n, rp, ci, va = gen.rmat_pagerank_csr(scale, ef, seed, "cpu")
+    x = gen.vector_pm1(n, seed + 50, "cpu").numpy()
+    check_plan(sp, orc, cuda, n, n, rp.numpy(), ci.numpy(), va.numpy(), x, caps=(4, 64, 1000), what=f"rmat {scale}",
+               expect_mode=1)
+    # device maximum: at these sizes every column fits -> the table is x itself
+    check_plan(sp, orc, cuda, n, n, rp.numpy(), ci.numpy(), va.numpy(), x, caps=(0,), what=f"rmat {scale} all",
+               expect_mode=2 if n <= 49152 else 1)
+
+
+@pytest.mark.parametrize("rows,cols,avg,skew,seed", [
+    (1, 1, 1, 0.0, 1), (5000, 70000, 9, 0.3, 2), (70000, 70000, 3, 0.05, 3), (300, 100000, 700, 0.0, 4),
+    (100003, 65537, 3, 0.0, 5), (20000, 20000, 40, 0.5, 6)])
+def test_random_shapes(sp, orc, cuda, rows, cols, avg, skew, seed):
+    gen = gen_mod()
+    rp, ci, va = gen.random_csr(rows, cols, avg, seed, "cpu", skew)
+    x = gen.vector_pm1(cols, seed + 100, "cpu").numpy()
+    check_plan(sp, orc, cuda, rows, cols, rp.numpy(), ci.numpy(), va.numpy(), x, caps=(8, 512, 0),
+               what=f"random {rows}x{cols}")
+
+
+def test_tile_geometry_edge_cases(sp, orc, cuda):
+    """Rows far longer than a tile (tiles without a single row end, 513 load groups when the span
+    starts unaligned), empty rows before / between / after, nnz not a multiple of 4, a single row."""
+    rng = np.random.default_rng(7)
+    cols = 60000
+    for lens in ([100001], [1, 50003, 0, 0, 50002], [0, 0, 70001, 0], [3, 90001, 1], [2047, 2049, 1, 4095],
+                 [0] * 3000 + [7] + [0] * 3000, [5] * 10000):
+        lens = np.array(lens)
+        rp = np.zeros(len(lens) + 1, np.int32)
+        rp[1:] = np.cumsum(lens)
+        nnz = int(rp[-1])
+        # hub-heavy columns: half of the entries fall on 32 columns
+        hub = rng.integers(0, 32, nnz) * 1777
+        cold = rng.integers(0, cols, nnz)
+        ci = np.where(rng.random(nnz) < 0.5, hub, cold).astype(np.int32)
+        for r in range(len(lens)):
+            ci[rp[r]:rp[r + 1]].sort()
+        va = rng.uniform(-1, 1, nnz).astype(np.float32)
+        x = rng.uniform(-1, 1, cols).astype(np.float32)
+        check_plan(sp, orc, cuda, len(lens), cols, rp, ci, va, x, caps=(16, 40), what=f"lens {lens[:5].tolist()}",
+                   expect_mode=1 if nnz > 1000 else None)
+
+
+def test_unaligned_values_pointer(sp, orc, cuda):
+    gen = gen_mod()
+    rows, cols = 30000, 80000
+    rp, ci, va = gen.random_csr(rows, cols, 7, 31, "cpu", 0.2)
+    x = gen.vector_pm1(cols, 32, "cpu")
+    y64, scale = orc.spmv_csr_f64(rows, rp.numpy(), ci.numpy(), va.numpy(), x.numpy())
+    pad = lambda t: torch.cat([torch.zeros(1, dtype=t.dtype), t]).to(cuda)[1:]  # noqa: E731
+    d_rp, d_ci, d_va, d_x = pad(rp), pad(ci), pad(va), pad(x)
+    A = sp.DeviceCSR(rows, cols, d_rp, d_ci, d_va)
+    for cap in (100, 0):  # hub table with unaligned values; cap 0 -> device maximum
+        plan = sp.CsrPlan(A.ptr, cap, force=True)
+        d_y = torch.zeros(rows + 1, dtype=torch.float32, device=cuda)[1:]
+        assert plan.spmv(d_x, d_y) == 0
+        torch.cuda.synchronize()
+        assert_within_tolerance(d_y.cpu().numpy(), y64, scale, f"unaligned cap {cap}")
+        plan.close()
+
+
+def test_values_are_read_live_and_plan_follows_uploads(sp, orc, cuda):
+    """The plan re-encodes col_indices only: new values in the same pattern need no new plan."""
+    gen = gen_mod()
+    n, rp, ci, va = gen.rmat_pagerank_csr(14, 16, 9, cuda)
+    A = sp.DeviceCSR(n, n, rp, ci, va)
+    x = gen.vector_pm1(n, 3, cuda)
+    plan = sp.CsrPlan(A.ptr, 256, force=True)
+    va.mul_(-2.5)
+    y = torch.empty(n, device=cuda)
+    assert plan.spmv(x, y) == 0
+    y_plain = plain_merge(sp, A, x, n, n)
+    assert np.array_equal(bits(y.cpu().numpy()), bits(y_plain))
+    plan.close()
+
+
+def test_pagerank_with_and_without_hub_table(sp, orc, cuda):
+    """The fused PageRank iteration through the hub-table kernel: same ranks (L1 <= 1e-6 against
+    the f64 restatement of the reference recurrence, src/pagerank.cu:93-150) and the same residuals
+    as through the plain tile kernel."""
+    gen = gen_mod()
+    import gpu_spmv_b200.dist as D
+    n, rp, ci, va = gen.rmat_pagerank_csr(16, 16, 11, cuda)
+    iters = 12
+    outs = []
+    for cap in (0, 300, -1):
+        shard = D.CudaShard(n, 0, rp, ci, va)
+        used = shard.set_hot(cap, force=True)
+        assert (used == 0) == (cap == 0)
+        out = D.pagerank_sharded(shard, [0, n], 0.85, 0.0, iters, fixed_iterations=iters)
+        outs.append((out.ranks.cpu().numpy(), out.final_residual, out.l1_residual))
+        shard.close()
+    o_ranks, _, o_l2, o_l1, _ = orc.pagerank_f64(n, n, rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy(), 0.85, 0.0,
+                                                 iters, fixed_it=iters)
+    for ranks, l2, l1 in outs:
+        assert np.abs(ranks.astype(np.float64) - o_ranks).sum() <= 1e-6
+        assert abs(l2 - o_l2) <= 1e-8 + 1e-3 * o_l2 and abs(l1 - o_l1) <= 1e-8 + 1e-3 * o_l1
+    for ranks, _, _ in outs[1:]:  # the table changes nothing in the row arithmetic (only the order of the f64 sums)
+        assert np.abs(ranks.astype(np.float64) - outs[0][0]).sum() <= 1e-9
+
+
+def test_spmv_csr_attaches_a_plan_to_csr_to_gpu_uploads(sp, orc, cuda):
+    """Drop-in path: spmv_csr(MERGE_PATH) on arrays uploaded by csr_to_gpu builds the plan on the
+    second call (large scale-free matrix), later calls run the hub-table kernel with identical
+    results; csr_forget_plan / csr_free_gpu drop it."""
+    from gpu_helpers import GpuCSR, run_csr
+    gen = gen_mod()
+    n, rp, ci, va = gen.rmat_pagerank_csr(19, 16, 21, "cpu")
+    x = gen.vector_pm1(n, 5, "cpu").numpy()
+    A = GpuCSR(sp, n, n, rp.numpy(), ci.numpy(), va.numpy())
+    y64, scale = orc.spmv_csr_f64(n, A.rp, A.ci, A.va, x)
+    y1, _ = run_csr(sp, A.mat, x, MERGE, cuda, n)
+    assert sp.csr_auto_plan_info(A.mat) == (0, 0)
+    y2, _ = run_csr(sp, A.mat, x, MERGE, cuda, n)
+    hot_columns, hot_nnz = sp.csr_auto_plan_info(A.mat)
+    assert hot_columns > 0 and hot_nnz * 8 >= len(A.ci)
+    y3, res = run_csr(sp, A.mat, x, MERGE, cuda, n)
+    assert_within_tolerance(y1, y64, scale, "first call")
+    assert np.array_equal(bits(y1), bits(y2)) and np.array_equal(bits(y1), bits(y3))
+    assert res.elapsed_ms > 0
+    sp.csr_forget_plan(A.mat)
+    assert sp.csr_auto_plan_info(A.mat) == (0, 0)
+    y4, _ = run_csr(sp, A.mat, x, MERGE, cuda, n)
+    assert np.array_equal(bits(y1), bits(y4))
+    A.close()
