@@ -434,6 +434,16 @@ def launch_count():
     return int(lib.spmv_b200_launch_count())
 
 
+def csr_from_coo_device(out, rows, cols, d_rows, d_cols, d_vals):
+    """Device COO (torch int32 / int32 / float32 tensors) -> device CSR in `out` (a csr_create handle)."""
+    return lib.spmv_b200_csr_from_coo_device(out, int(rows), int(cols), int(d_vals.numel()), dptr(d_rows), dptr(d_cols),
+                                             dptr(d_vals))
+
+
+def csr_normalize_columns_device(A):
+    return lib.spmv_b200_csr_normalize_columns_device(A)
+
+
 class CsrPlan:
     """Merge coordinates + hub-column table of a device CSR (spmv_b200_csr_plan)."""
 

@@ -143,6 +143,8 @@ PROTOTYPES = {
     "spmv_b200_merge_path_search": (C.c_int, [C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p]),
     "spmv_b200_partition_rows": (C.c_int, [c_int_p, C.c_int, C.c_int, c_int_p]),
     "spmv_b200_partition_rows_weighted": (C.c_int, [c_int_p, C.c_int, C.c_int, C.c_int, c_int_p]),
+    "spmv_b200_csr_from_coo_device": (C.c_int, [CSR_P, C.c_int, C.c_int, C.c_longlong, vp, vp, vp]),
+    "spmv_b200_csr_normalize_columns_device": (C.c_int, [CSR_P]),
     "spmv_b200_csr_plan_create": (C.c_int, [CSR_P, C.c_int, C.c_int, C.POINTER(vp)]),
     "spmv_b200_csr_plan_destroy": (None, [vp]),
     "spmv_b200_csr_plan_info": (C.c_int, [vp, c_int_p, C.POINTER(C.c_longlong), c_int_p]),

@@ -352,6 +352,16 @@ int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, int parts, int* 
     return spmv_b200_partition_rows_weighted(row_ptrs, num_rows, parts, 0, bounds);
 }
 
+int spmv_b200_csr_from_coo_device(spmv_b200_csr* out, int rows, int cols, long long n_entries, const int* d_row_indices,
+                                  const int* d_col_indices, const float* d_values) {
+    return guarded([&] {
+        return b200::csr_from_coo_device(cpp(out), rows, cols, n_entries, d_row_indices, d_col_indices, d_values);
+    });
+}
+int spmv_b200_csr_normalize_columns_device(spmv_b200_csr* A) {
+    return guarded([&] { return b200::csr_normalize_columns_device(cpp(A)); });
+}
+
 int spmv_b200_csr_plan_create(const spmv_b200_csr* A, int max_hot_columns, int force, spmv_b200_csr_plan** out) {
     return guarded([&] {
         return b200::csr_plan_create(cpp(A), max_hot_columns, force != 0, reinterpret_cast<b200::CsrPlan**>(out));

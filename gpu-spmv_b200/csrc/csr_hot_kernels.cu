@@ -444,6 +444,8 @@ cudaError_t run_hot(const CsrView& A, const HotPlan& hot, const float* x, const 
 
 // ------------------------------------------------------------------------ host side ----
 
+int device_sm_count() { return device_sms(); }
+
 int hot_capacity() {
     int dev_id = 0, optin = 0;
     cudaGetDevice(&dev_id);
@@ -478,33 +480,18 @@ void hot_plan_release(HotPlan* p) {
     *p = HotPlan();
 }
 
-cudaError_t hot_plan_build(const CsrView& A, HotPlan* out, int capacity, bool force, cudaStream_t stream) {
-    *out = HotPlan();
-    out->nnz = A.nnz;
-    out->cols = A.cols;
-    const int device_cap = hot_capacity();
-    const bool whole_x = A.cols <= (capacity > 0 ? (capacity < device_cap ? capacity : device_cap) : device_cap);
-    if (capacity <= 0) capacity = hot_default_capacity();
-    if (capacity > device_cap) capacity = device_cap;
-    if (A.rows <= 0 || A.nnz <= 0 || A.cols <= 0 || capacity < 4) return cudaSuccess;
-    if (!force && !hot_worthwhile(A)) return cudaSuccess;
-    if (whole_x) {  // x itself is the table: no global gather is left, so the size costs nothing
-        out->all_hot = true;
-        out->n_hot = A.cols;
-        out->hot_nnz = A.nnz;
-        return cudaSuccess;
-    }
-    // A hub column is fetched once per CTA, so it must be referenced more often than there are CTAs
-    const int t_min = force ? 2 : 2 * device_sms();
-
+// The `capacity` most referenced columns (reference count >= t_min): *d_slot_of (device int[cols],
+// caller frees) maps a column to its table slot or -1, *d_hot_cols (device int[capacity], caller
+// frees) is the inverse.  Synchronises `stream`.
+cudaError_t hot_select_columns(const CsrView& A, int capacity, int t_min, int** d_slot_of, int** d_hot_cols_out,
+                               int* n_hot_out, long long* hot_nnz_out, cudaStream_t stream) {
     int* d_counts = nullptr;
     unsigned* d_hist = nullptr;
     int* d_small = nullptr;  // [0] threshold, [1] admitted, [2..3] hot nnz (64-bit)
-    int* d_enc = nullptr;
     int* d_hot_cols = nullptr;
     auto fail = [&](cudaError_t e) {
         cudaGetLastError();
-        cudaFree(d_counts); cudaFree(d_hist); cudaFree(d_small); cudaFree(d_enc); cudaFree(d_hot_cols);
+        cudaFree(d_counts); cudaFree(d_hist); cudaFree(d_small); cudaFree(d_hot_cols);
         return e;
     };
     cudaError_t e;
@@ -525,26 +512,61 @@ cudaError_t hot_plan_build(const CsrView& A, HotPlan* out, int capacity, bool fo
     int h_small[4] = {0, 0, 0, 0};
     if ((e = cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return fail(e);
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return fail(e);
-    const int n_hot = h_small[1] < capacity ? h_small[1] : capacity;
     unsigned long long hot_nnz = 0;
     memcpy(&hot_nnz, h_small + 2, sizeof(hot_nnz));
-    // worth it when the table takes a real share of the gathers off the L1
-    const bool useful = n_hot > 0 && (force || hot_nnz * 8ull >= static_cast<unsigned long long>(A.nnz));
-    if (!useful) {
-        fail(cudaSuccess);
-        return cudaSuccess;
-    }
-    if ((e = cudaMalloc(&d_enc, sizeof(int) * static_cast<size_t>(A.nnz))) != cudaSuccess) return fail(e);
-    hot_encode_kernel<<<plan_grid(A.nnz), kPlanBlock, 0, stream>>>(A.nnz, A.cols, A.col_indices, d_counts, d_enc);
-    count_launches(1);
-    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return fail(e);
-    cudaFree(d_counts);
     cudaFree(d_hist);
     cudaFree(d_small);
+    *d_slot_of = d_counts;
+    *d_hot_cols_out = d_hot_cols;
+    *n_hot_out = h_small[1] < capacity ? h_small[1] : capacity;
+    *hot_nnz_out = static_cast<long long>(hot_nnz);
+    return cudaSuccess;
+}
+
+cudaError_t hot_plan_build(const CsrView& A, HotPlan* out, int capacity, bool force, cudaStream_t stream,
+                           int min_share) {
+    *out = HotPlan();
+    out->nnz = A.nnz;
+    out->cols = A.cols;
+    const int device_cap = hot_capacity();
+    const bool whole_x = A.cols <= (capacity > 0 ? (capacity < device_cap ? capacity : device_cap) : device_cap);
+    if (capacity <= 0) capacity = hot_default_capacity();
+    if (capacity > device_cap) capacity = device_cap;
+    if (A.rows <= 0 || A.nnz <= 0 || A.cols <= 0 || capacity < 4) return cudaSuccess;
+    if (!force && !hot_worthwhile(A)) return cudaSuccess;
+    if (whole_x) {  // x itself is the table: no global gather is left, so the size costs nothing
+        out->all_hot = true;
+        out->n_hot = A.cols;
+        out->hot_nnz = A.nnz;
+        return cudaSuccess;
+    }
+    // A hub column is fetched once per CTA, so it must be referenced more often than there are CTAs
+    const int t_min = force ? 2 : 2 * device_sms();
+    int* d_slot_of = nullptr;
+    int* d_hot_cols = nullptr;
+    int n_hot = 0;
+    long long hot_nnz = 0;
+    cudaError_t e = hot_select_columns(A, capacity, t_min, &d_slot_of, &d_hot_cols, &n_hot, &hot_nnz, stream);
+    if (e != cudaSuccess) return e;
+    // worth it when the table takes a real share of the gathers off the L1
+    const bool useful = n_hot > 0 && (force || hot_nnz * min_share >= static_cast<long long>(A.nnz));
+    int* d_enc = nullptr;
+    if (useful && (e = cudaMalloc(&d_enc, sizeof(int) * static_cast<size_t>(A.nnz))) == cudaSuccess) {
+        hot_encode_kernel<<<plan_grid(A.nnz), kPlanBlock, 0, stream>>>(A.nnz, A.cols, A.col_indices, d_slot_of, d_enc);
+        count_launches(1);
+        e = cudaStreamSynchronize(stream);
+    }
+    cudaFree(d_slot_of);
+    if (!useful || e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(d_enc);
+        cudaFree(d_hot_cols);
+        return useful ? e : cudaSuccess;
+    }
     out->enc = d_enc;
     out->hot_cols = d_hot_cols;
     out->n_hot = n_hot;
-    out->hot_nnz = static_cast<long long>(hot_nnz);
+    out->hot_nnz = hot_nnz;
     return cudaSuccess;
 }
 

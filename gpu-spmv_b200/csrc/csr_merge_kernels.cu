@@ -339,11 +339,6 @@ reduce_partials_kernel(const double* __restrict__ partials, int count, double* _
     }
 }
 
-__global__ void zero_rows_kernel(int rows, float* __restrict__ y) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < rows) y[i] = 0.0f;
-}
-
 int merge_env_int(const char* name, int fallback) {
     const char* v = getenv(name);
     return v ? atoi(v) : fallback;
@@ -402,6 +397,12 @@ cudaError_t launch_merge_fixup_pagerank(const MergePlan& plan, const PageRankSte
                                                                            plan.carry_val, op, plan.partials, partial_base);
     reduce_partials_kernel<<<1, 1024, 0, stream>>>(plan.partials, partial_base + plan.fixup_blocks, args.out);
     count_launches(2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_partials(const double* partials, int count, double* out, cudaStream_t stream) {
+    reduce_partials_kernel<<<1, 1024, 0, stream>>>(partials, count, out);
+    count_launches(1);
     return cudaGetLastError();
 }
 

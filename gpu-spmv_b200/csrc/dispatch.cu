@@ -54,18 +54,21 @@ void* Scratch::reserve(size_t bytes) {
 }
 
 cudaError_t dispatch_csr(const CsrView& A, const float* x, float* y, int kernel_type, Scratch& scratch,
-                         cudaStream_t stream, const HotPlan* hot) {
+                         cudaStream_t stream, const PlannedCsr* planned) {
     if (A.rows <= 0) return cudaSuccess;
     switch (kernel_type) {
         case SpMVConfig::MERGE_PATH: {
             if (A.nnz <= 0) return launch_csr_stream(A, x, y, 1, stream);  // writes zeros
+            if (planned && planned->seg.valid() && planned->seg.nnz == A.nnz && planned->seg.rows == A.rows &&
+                planned->seg.cols == A.cols)
+                return launch_seg_spmv(A, planned->seg, x, y, stream);
             void* block = scratch.reserve(merge_plan_bytes(A.rows, A.nnz, false));
             if (!block) return cudaErrorMemoryAllocation;
             const MergePlan plan = merge_plan_carve(block, A.rows, A.nnz, false);
             cudaError_t e = launch_merge_partition(A, plan, stream);
             if (e != cudaSuccess) return e;
-            if (hot && (hot->n_hot > 0) && hot->nnz == A.nnz && hot->cols == A.cols)
-                return launch_hot_spmv(A, *hot, x, y, plan, stream);
+            if (planned && planned->hot.n_hot > 0 && planned->hot.nnz == A.nnz && planned->hot.cols == A.cols)
+                return launch_hot_spmv(A, planned->hot, x, y, plan, stream);
             return launch_merge_spmv(A, x, y, plan, stream);
         }
         case SpMVConfig::VECTOR_CSR:
@@ -80,10 +83,33 @@ cudaError_t dispatch_csr(const CsrView& A, const float* x, float* y, int kernel_
 // Explicit plan (additive API): merge coordinates computed once + the hub-column plan.
 struct CsrPlan {
     CsrView A{};
-    HotPlan hot;
+    PlannedCsr planned;
     Scratch merge_block;
     MergePlan merge;
 };
+
+// SPMV_B200_PLAN=hub|seg forces one of the planned kernels (tuning / tests); default: by structure
+static int plan_kind_env() {
+    static const int kind = [] {
+        const char* v = getenv("SPMV_B200_PLAN");
+        return !v ? 0 : (v[0] == 'h' ? 1 : (v[0] == 's' ? 2 : 0));
+    }();
+    return kind;
+}
+
+cudaError_t planned_build(const CsrView& A, PlannedCsr* out, int capacity, bool force, bool allow_seg,
+                          cudaStream_t stream) {
+    out->release();
+    if (A.rows <= 0 || A.nnz <= 0) return cudaSuccess;
+    const int kind = plan_kind_env();
+    if (kind == 2) return seg_plan_build(A, &out->seg, capacity, force, stream);
+    // measured on R-MAT 24 / 26 and the Laplacian (profiles/r1_hub_kernel.md): the hub-column kernel wins
+    // on scale-free matrices (and overlaps the PageRank slice exchange), the segmented stream elsewhere
+    cudaError_t e = hot_plan_build(A, &out->hot, capacity, force, stream, kind == 1 ? 8 : 4);
+    if (e != cudaSuccess || out->hot.n_hot > 0 || kind == 1 || !allow_seg) return e;
+    if (static_cast<long long>(A.nnz) < 4ll * A.rows && !force) return cudaSuccess;
+    return seg_plan_build(A, &out->seg, capacity, force, stream);
+}
 
 int csr_plan_create(const CSRMatrix* A, int max_hot_columns, bool force, CsrPlan** out) {
     if (!A || !out) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
@@ -101,11 +127,11 @@ int csr_plan_create(const CSRMatrix* A, int max_hot_columns, bool force, CsrPlan
         }
         p->merge = merge_plan_carve(block, p->A.rows, p->A.nnz, false);
         cudaError_t e = launch_merge_partition(p->A, p->merge, stream);
-        if (e == cudaSuccess) e = hot_plan_build(p->A, &p->hot, max_hot_columns, force, stream);
+        if (e == cudaSuccess) e = planned_build(p->A, &p->planned, max_hot_columns, force, true, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            hot_plan_release(&p->hot);
+            p->planned.release();
             delete p;
             return static_cast<int>(e == cudaErrorMemoryAllocation ? SpMVError::CUDA_MALLOC : SpMVError::KERNEL_LAUNCH);
         }
@@ -116,14 +142,18 @@ int csr_plan_create(const CSRMatrix* A, int max_hot_columns, bool force, CsrPlan
 
 void csr_plan_destroy(CsrPlan* p) {
     if (!p) return;
-    hot_plan_release(&p->hot);
+    p->planned.release();
     delete p;
 }
 
 void csr_plan_info(const CsrPlan* p, int* hot_columns, long long* hot_nnz, int* mode) {
-    if (hot_columns) *hot_columns = p ? p->hot.n_hot : 0;
-    if (hot_nnz) *hot_nnz = p ? p->hot.hot_nnz : 0;
-    if (mode) *mode = !p || p->hot.n_hot <= 0 ? 0 : (p->hot.all_hot ? 2 : 1);
+    const bool seg = p && p->planned.seg.valid();
+    if (hot_columns) *hot_columns = !p ? 0 : (seg ? p->planned.seg.n_hot : p->planned.hot.n_hot);
+    if (hot_nnz) *hot_nnz = !p ? 0 : (seg ? p->planned.seg.hot_nnz : p->planned.hot.hot_nnz);
+    if (mode) {
+        if (seg) *mode = p->planned.seg.whole_x ? 4 : 3;
+        else *mode = !p || p->planned.hot.n_hot <= 0 ? 0 : (p->planned.hot.all_hot ? 2 : 1);
+    }
 }
 
 int spmv_csr_planned(const CsrPlan* p, const float* d_x, float* d_y, cudaStream_t stream) {
@@ -132,7 +162,8 @@ int spmv_csr_planned(const CsrPlan* p, const float* d_x, float* d_y, cudaStream_
     if (A.rows <= 0) return 0;
     cudaError_t e;
     if (A.nnz <= 0) e = launch_csr_stream(A, d_x, d_y, 1, stream);  // writes zeros
-    else if (p->hot.n_hot > 0) e = launch_hot_spmv(A, p->hot, d_x, d_y, p->merge, stream);
+    else if (p->planned.seg.valid()) e = launch_seg_spmv(A, p->planned.seg, d_x, d_y, stream);
+    else if (p->planned.hot.n_hot > 0) e = launch_hot_spmv(A, p->planned.hot, d_x, d_y, p->merge, stream);
     else e = launch_merge_spmv(A, d_x, d_y, p->merge, stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -150,7 +181,7 @@ struct AutoEntry {
     int rows = 0, nnz = 0;
     int calls = 0;
     bool tried = false;
-    HotPlan hot;
+    PlannedCsr planned;
 };
 std::mutex g_auto_mu;
 std::unordered_map<const void*, AutoEntry*> g_auto;
@@ -169,7 +200,7 @@ void note_device_csr(const CSRMatrix* A) {
     std::lock_guard<std::mutex> lock(g_auto_mu);
     AutoEntry*& e = g_auto[A->d_col_indices];
     if (e) {
-        hot_plan_release(&e->hot);
+        e->planned.release();
         delete e;
     }
     e = new AutoEntry();
@@ -182,7 +213,7 @@ void forget_device_csr(const void* d_col_indices) {
     std::lock_guard<std::mutex> lock(g_auto_mu);
     auto it = g_auto.find(d_col_indices);
     if (it == g_auto.end()) return;
-    hot_plan_release(&it->second->hot);
+    it->second->planned.release();
     delete it->second;
     g_auto.erase(it);
 }
@@ -195,12 +226,13 @@ void auto_plan_info(const CSRMatrix* A, int* hot_columns, long long* hot_nnz) {
     std::lock_guard<std::mutex> lock(g_auto_mu);
     auto it = g_auto.find(A->d_col_indices);
     if (it == g_auto.end()) return;
-    if (hot_columns) *hot_columns = it->second->hot.n_hot;
-    if (hot_nnz) *hot_nnz = it->second->hot.hot_nnz;
+    const PlannedCsr& pl = it->second->planned;
+    if (hot_columns) *hot_columns = pl.seg.valid() ? (pl.seg.n_hot > 0 ? pl.seg.n_hot : 1) : pl.hot.n_hot;
+    if (hot_nnz) *hot_nnz = pl.seg.valid() ? pl.seg.hot_nnz : pl.hot.hot_nnz;
 }
 
 // nullptr: no plan (not an upload of ours, first call, or not worthwhile)
-static const HotPlan* auto_hot_plan(const CSRMatrix* A, cudaStream_t stream) {
+static const PlannedCsr* auto_planned(const CSRMatrix* A, cudaStream_t stream) {
     if (hot_env_mode() == 0 || !A->d_col_indices) return nullptr;
     std::lock_guard<std::mutex> lock(g_auto_mu);
     auto it = g_auto.find(A->d_col_indices);
@@ -209,12 +241,12 @@ static const HotPlan* auto_hot_plan(const CSRMatrix* A, cudaStream_t stream) {
     if (e->rows != A->num_rows || e->nnz != A->nnz) return nullptr;  // the struct was edited by hand
     if (!e->tried && e->calls++ >= 1) {
         e->tried = true;
-        if (hot_plan_build(view_of(A), &e->hot, 0, hot_env_mode() > 0, stream) != cudaSuccess) {
+        if (planned_build(view_of(A), &e->planned, 0, hot_env_mode() > 0, true, stream) != cudaSuccess) {
             cudaGetLastError();
-            hot_plan_release(&e->hot);
+            e->planned.release();
         }
     }
-    return e->hot.n_hot > 0 ? &e->hot : nullptr;
+    return e->planned.any() ? &e->planned : nullptr;
 }
 
 namespace {
@@ -310,10 +342,10 @@ SpMVResult spmv_csr(const CSRMatrix* A, const float* d_x, float* d_y, const SpMV
     if (!ctx) return b200::failed(SpMVError::KERNEL_LAUNCH);  // no usable device: fail, never compute on the host
 
     cudaStream_t stream = nullptr;  // legacy default stream, as the reference
-    const b200::HotPlan* hot =
-        kernel == static_cast<int>(SpMVConfig::MERGE_PATH) ? b200::auto_hot_plan(A, stream) : nullptr;
+    const b200::PlannedCsr* plan =
+        kernel == static_cast<int>(SpMVConfig::MERGE_PATH) ? b200::auto_planned(A, stream) : nullptr;
     cudaEventRecord(ctx->start, stream);
-    cudaError_t e = b200::dispatch_csr(b200::view_of(A), d_x, d_y, kernel, ctx->scratch, stream, hot);
+    cudaError_t e = b200::dispatch_csr(b200::view_of(A), d_x, d_y, kernel, ctx->scratch, stream, plan);
     cudaEventRecord(ctx->stop, stream);
     cudaError_t sync = cudaEventSynchronize(ctx->stop);
     cudaError_t last = cudaGetLastError();

@@ -146,12 +146,63 @@ int hot_default_capacity();           // table slots used when the caller does n
 bool hot_worthwhile(const CsrView& A);  // large enough for the persistent grid
 // Builds the plan (synchronises `stream`).  capacity <= 0: the device maximum.  Success with
 // n_hot == 0 means "use the plain tile kernel".  force skips the size / benefit thresholds (tests).
-cudaError_t hot_plan_build(const CsrView& A, HotPlan* plan, int capacity, bool force, cudaStream_t stream);
+// min_share: the table must serve at least nnz / min_share non-zeros for the plan to be kept.
+cudaError_t hot_plan_build(const CsrView& A, HotPlan* plan, int capacity, bool force, cudaStream_t stream,
+                           int min_share = 8);
+// the selection step alone (shared with csr_seg_kernels.cu); see the definition
+cudaError_t hot_select_columns(const CsrView& A, int capacity, int t_min, int** d_slot_of, int** d_hot_cols,
+                               int* n_hot, long long* hot_nnz, cudaStream_t stream);
+int device_sm_count();
 void hot_plan_release(HotPlan* plan);
 cudaError_t launch_hot_spmv(const CsrView& A, const HotPlan& hot, const float* x, float* y, const MergePlan& plan,
                             cudaStream_t stream);
 cudaError_t launch_hot_pagerank(const CsrView& A, const HotPlan& hot, const MergePlan& plan,
                                 const PageRankStepArgs& args, cudaStream_t stream);
+
+// ---- segmented-stream plan (csr_seg_kernels.cu): row heads travel with the re-encoded stream ----
+constexpr int kSegTile = 2048;  // non-zeros per tile
+struct SegPlan {
+    int n_hot = 0;                  // entries of the shared-memory x table (0: every gather is global)
+    bool whole_x = false;           // the table is x itself (cols <= capacity)
+    long long hot_nnz = 0;          // non-zeros served by the table
+    int* enc = nullptr;             // device [num_tiles * kSegTile]: hub bit | head bit | slot or column
+    int* hot_cols = nullptr;        // device [n_hot] column of every slot (nullptr when whole_x)
+    int* rows_nz = nullptr;         // device [nonempty_rows] row of the k-th head
+    int* tile_head_base = nullptr;  // device [8 * num_tiles + 1] heads before every 256-non-zero span
+    uint32_t* nonempty = nullptr;   // device bit mask over rows
+    float* tile_lead = nullptr;     // device [num_tiles] work arrays of a product (one product at a time)
+    float* tile_tail = nullptr;
+    double* partials = nullptr;     // device [3 * epilogue_blocks] PageRank sums
+    int num_tiles = 0, nonempty_rows = 0, epilogue_blocks = 0;
+    int rows = 0, cols = 0, nnz = 0;
+    bool valid() const { return enc != nullptr; }
+};
+int seg_table_capacity();
+int seg_default_capacity();
+bool seg_worthwhile(const CsrView& A);
+// Builds the plan (synchronises `stream`).  capacity <= 0: tuned default.  Success with
+// !plan->valid() means "not worthwhile, use the merge-path kernels".  force skips the thresholds.
+cudaError_t seg_plan_build(const CsrView& A, SegPlan* plan, int capacity, bool force, cudaStream_t stream);
+void seg_plan_release(SegPlan* plan);
+cudaError_t launch_seg_spmv(const CsrView& A, const SegPlan& plan, const float* x, float* y, cudaStream_t stream);
+cudaError_t launch_seg_pagerank(const CsrView& A, const SegPlan& plan, const PageRankStepArgs& args, cudaStream_t stream);
+// What a plan holds for the planned kernels: at most one of the two is filled.
+struct PlannedCsr {
+    HotPlan hot;  // scale-free matrices: hub-column merge-path kernel (csr_hot_kernels.cu)
+    SegPlan seg;  // other matrices with >= 4 non-zeros per row: segmented-stream kernel (csr_seg_kernels.cu)
+    bool any() const { return seg.valid() || hot.n_hot > 0; }
+    void release() {
+        hot_plan_release(&hot);
+        seg_plan_release(&seg);
+    }
+};
+// Chooses by measured structure (SPMV_B200_PLAN=hub|seg forces one): the hub-column plan when
+// its table would serve >= 1/4 of the non-zeros, else -- if allow_seg -- the segmented-stream plan
+// when rows average >= 4 non-zeros, else nothing (plain merge-path).  Synchronises `stream`.
+cudaError_t planned_build(const CsrView& A, PlannedCsr* out, int capacity, bool force, bool allow_seg,
+                          cudaStream_t stream);
+// out[3] = ordered sum of `count` triples of per-CTA partial sums
+cudaError_t launch_reduce_partials(const double* partials, int count, double* out, cudaStream_t stream);
 
 // PageRank helpers
 cudaError_t launch_colsum(const CsrView& A, float* d_colsum, cudaStream_t stream);
@@ -166,11 +217,21 @@ cudaError_t launch_ell_from_csr(const CsrView& A, int width, float* ell_values, 
                                 cudaStream_t stream);
 cudaError_t launch_max_row_len(const CsrView& A, int* d_out, cudaStream_t stream);
 
+// ---- device-side assembly (assembly.cu) --------------------------------------------------
+// (row, col, value) triplets in device memory -> device CSR sorted by (row, col), duplicates kept
+// in input order; `out` receives the device arrays (csr_to_gpu ownership rules) and host arrays
+// of the right size for csr_from_gpu.
+int csr_from_coo_device(CSRMatrix* out, int rows, int cols, long long n_entries, const int* d_rows,
+                        const int* d_cols, const float* d_vals);
+// values[j] /= column sum (columns summing to 0 untouched): the column-normalised adjacency
+// matrix pagerank() expects (reference include/spmv/pagerank.h:28)
+int csr_normalize_columns_device(CSRMatrix* A);
+
 // ---- stream-ordered dispatch used by the blocking API, benchmark and PageRank --------
 // Chooses and launches the kernel(s) for `kernel_type` (any unknown value ->
 // SCALAR, as src/spmv_kernels.cu:287-288).  `scratch` backs merge-path plans.
 cudaError_t dispatch_csr(const CsrView& A, const float* x, float* y, int kernel_type,
-                         Scratch& scratch, cudaStream_t stream, const HotPlan* hot = nullptr);
+                         Scratch& scratch, cudaStream_t stream, const PlannedCsr* plan = nullptr);
 
 // ---- explicit CSR plans (dispatch.cu): merge coordinates + hub-column plan, built once ------
 struct CsrPlan;

@@ -39,8 +39,11 @@ struct PrPlan {
     MergePlan merge;
     Scratch tmp_block;   // kTmpDoubles doubles
     double* tmp = nullptr;
-    HotPlan hot;         // hub columns of the shard (csr_hot_kernels.cu); n_hot == 0: plain tile kernel
-    ~PrPlan() { hot_plan_release(&hot); }
+    // Hub-column plan of the shard when it is scale-free (the tile epilogue of that kernel also
+    // overlaps the slice exchange with the product: 1.17 vs 1.46 ms per iteration on 8 GPUs against
+    // the segmented-stream kernel, whose exchange is a separate pass); neither: plain tile kernel.
+    PlannedCsr planned;
+    ~PrPlan() { planned.release(); }
 };
 
 static int pr_hot_env() {
@@ -75,9 +78,9 @@ int pr_plan_create(const CSRMatrix* shard, int row_offset, int n_global, cudaStr
         return static_cast<int>(SpMVError::KERNEL_LAUNCH);
     }
     // the matrix is constant over the iterations: the hub-column plan pays for itself after a few
-    if (pr_hot_env() != 0 && hot_plan_build(p->A, &p->hot, 0, pr_hot_env() > 0, stream) != cudaSuccess) {
+    if (pr_hot_env() != 0 && planned_build(p->A, &p->planned, 0, pr_hot_env() > 0, false, stream) != cudaSuccess) {
         cudaGetLastError();
-        hot_plan_release(&p->hot);  // not fatal: the plain tile kernel is used
+        p->planned.release();  // not fatal: the plain tile kernel is used
     }
     *out = p;
     return 0;
@@ -90,14 +93,14 @@ void pr_plan_destroy(PrPlan* p) { delete p; }
 int pr_plan_set_hot(PrPlan* p, int max_hot_columns, bool force, cudaStream_t stream) {
     if (!p) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     cudaStreamSynchronize(stream);
-    hot_plan_release(&p->hot);
+    p->planned.release();
     if (max_hot_columns == 0) return 0;
-    if (hot_plan_build(p->A, &p->hot, max_hot_columns < 0 ? 0 : max_hot_columns, force, stream) != cudaSuccess) {
+    if (planned_build(p->A, &p->planned, max_hot_columns < 0 ? 0 : max_hot_columns, force, false, stream) != cudaSuccess) {
         cudaGetLastError();
-        hot_plan_release(&p->hot);
+        p->planned.release();
         return static_cast<int>(SpMVError::CUDA_MALLOC);
     }
-    return p->hot.n_hot;
+    return p->planned.seg.valid() ? (p->planned.seg.n_hot > 0 ? p->planned.seg.n_hot : 1) : p->planned.hot.n_hot;
 }
 
 int pr_step(PrPlan* p, const float* d_r_old, float* d_r_new, float damping, const float* d_dsum,
@@ -120,8 +123,9 @@ int pr_step(PrPlan* p, const float* d_r_old, float* d_r_new, float damping, cons
     a.d_dsum = d_dsum;
     a.bits = d_bits;
     a.out = d_partial;
-    const cudaError_t e = p->hot.n_hot > 0 ? launch_hot_pagerank(p->A, p->hot, p->merge, a, stream)
-                                           : launch_merge_pagerank(p->A, p->merge, a, stream);
+    const cudaError_t e = p->planned.seg.valid()     ? launch_seg_pagerank(p->A, p->planned.seg, a, stream)
+                          : p->planned.hot.n_hot > 0 ? launch_hot_pagerank(p->A, p->planned.hot, p->merge, a, stream)
+                                                     : launch_merge_pagerank(p->A, p->merge, a, stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return static_cast<int>(SpMVError::KERNEL_LAUNCH);

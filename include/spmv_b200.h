@@ -279,17 +279,35 @@ SPMV_B200_API int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, in
 SPMV_B200_API int spmv_b200_partition_rows_weighted(const int* row_ptrs, int num_rows, int parts,
                                                     int row_weight, int* bounds /* [parts+1] */);
 
+/* ---- device-side assembly ------------------------------ */
+
+/* (row, col, value) triplets in DEVICE memory -> CSR sorted by (row, col) in the device arrays of
+ * `out` (allocated here, owns_device_memory = true; duplicates are kept, in input order).  The
+ * reference can only assemble from a dense host array (csr_from_dense, src/csr_matrix.cpp:50-95).
+ * Host arrays of `out` are re-allocated to the new size (uninitialised) so that csr_from_gpu can
+ * fill them.  An index outside [0, rows) x [0, cols) -> INVALID_ARGUMENT, nothing is changed. */
+SPMV_B200_API int spmv_b200_csr_from_coo_device(spmv_b200_csr* out, int rows, int cols,
+                                                long long n_entries, const int* d_row_indices,
+                                                const int* d_col_indices, const float* d_values);
+/* d_values[j] /= sum of column d_col_indices[j] (columns summing to 0 are left alone): the
+ * column-normalised adjacency matrix pagerank() expects (include/spmv/pagerank.h:28). */
+SPMV_B200_API int spmv_b200_csr_normalize_columns_device(spmv_b200_csr* A);
+
 /* ---- CSR plans: merge coordinates + hub-column table, built once --------- */
 
 /*
  * Opaque plan over the DEVICE arrays of a CSR matrix for repeated MERGE_PATH products with the
  * same sparsity pattern (the "persistent workspace" the reference lacks: its spmv_csr recomputes
  * everything per call, src/spmv_kernels.cu:258-297).  It holds (1) the merge-path tile
- * coordinates and (2), for scale-free matrices, the hub-column plan of csr_hot_kernels.cu: the x
- * entries of the max_hot_columns most referenced columns are kept in shared memory by the kernel,
- * and a PRIVATE re-encoding of col_indices tells it which.  The caller's arrays are not modified;
+ * coordinates and (2) a PRIVATE re-encoding of col_indices for one of the two planned kernels,
+ * chosen by the measured structure: scale-free matrices (a table of the max_hot_columns most
+ * referenced columns would serve >= 1/4 of the non-zeros) get the hub-column merge-path kernel of
+ * csr_hot_kernels.cu, which keeps those x entries in shared memory; other matrices with >= 4
+ * non-zeros per row get the segmented-stream kernel of csr_seg_kernels.cu, whose re-encoding also
+ * carries the row starts.  The caller's arrays are not modified;
  * d_values is read live at every product, d_row_ptrs / d_col_indices must not change while the
- * plan is alive.  max_hot_columns <= 0: as many as fit next to the tile buffers (49152 on B200).
+ * plan is alive.  max_hot_columns <= 0: the tuned default (24576 on B200; the table competes with
+ * the L1 for the same 256 KB).
  * force != 0 skips the size / benefit thresholds (tests).
  */
 typedef struct spmv_b200_csr_plan spmv_b200_csr_plan;
@@ -297,11 +315,14 @@ SPMV_B200_API int spmv_b200_csr_plan_create(const spmv_b200_csr* A, int max_hot_
                                             spmv_b200_csr_plan** out);
 SPMV_B200_API void spmv_b200_csr_plan_destroy(spmv_b200_csr_plan* plan);
 /* hot_columns: table entries in use; hot_nnz: non-zeros served by the table;
- * mode: 0 plain tile kernel, 1 hub-column table, 2 the whole x fits the table */
+ * mode: 0 plain merge-path tile kernel with precomputed coordinates,
+ *       1 hub-column merge-path kernel, 2 the same with the whole x in the table,
+ *       3 segmented-stream kernel (csr_seg_kernels.cu), 4 the same with the whole x in the table */
 SPMV_B200_API int spmv_b200_csr_plan_info(const spmv_b200_csr_plan* plan, int* hot_columns,
                                           long long* hot_nnz, int* mode);
 /* y = A x through the plan; stream-ordered (stream is a cudaStream_t), no sync, no timing.
- * Bit-identical to spmv_csr(MERGE_PATH). */
+ * Deterministic; modes 0-2 are bit-identical to spmv_csr(MERGE_PATH), modes 3-4 sum in a
+ * different (fixed) order and agree within the fp32 SpMV tolerance. */
 SPMV_B200_API int spmv_b200_spmv_csr_planned(const spmv_b200_csr_plan* plan, const float* d_x,
                                              float* d_y, void* stream);
 /* spmv_csr(MERGE_PATH) attaches such a plan by itself to device arrays uploaded by csr_to_gpu

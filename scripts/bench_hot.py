@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--pagerank", action="store_true")
     ap.add_argument("--relabelled", action="store_true")
     ap.add_argument("--seed", type=int, default=44)
+    ap.add_argument("--dataset", default="rmat", choices=["rmat", "c2", "c3"])
     args = ap.parse_args()
 
     import numpy as np
@@ -38,8 +39,17 @@ def main():
     peak, _ = B.measured_peak()
     stream = torch.cuda.Stream()
     s_ptr = stream.cuda_stream
-    n, bounds, rp, ci, va, n_edges = B.build_rmat_shard(torch, gen, args.scale, 16, args.seed, 0, 1, dev,
-                                                        relabelled=args.relabelled)
+    if args.dataset == "c2":
+        n = 4096 * 4096
+        rp, ci, va = gen.laplacian_2d_csr(4096, dev)
+        bounds = [0, n]
+    elif args.dataset == "c3":
+        n = 50_000_000
+        rp, ci, va = gen.short_rows_with_outliers_csr(n, 43, dev)
+        bounds = [0, n]
+    else:
+        n, bounds, rp, ci, va, n_edges = B.build_rmat_shard(torch, gen, args.scale, 16, args.seed, 0, 1, dev,
+                                                            relabelled=args.relabelled)
     torch.cuda.synchronize()
     A = sp.DeviceCSR(n, n, rp, ci, va)
     x = gen.vector_pm1(n, 7, dev)
@@ -55,13 +65,13 @@ def main():
         assert sp.lib.spmv_b200_spmv_csr_async(A.ptr, sp.dptr(x), sp.dptr(y0), C.byref(cfg), C.c_void_p(s_ptr)) == 0
 
     r = B.bench_kernel(torch, sp, stream, plain, nbytes, args.steps, 3)
-    emit(what="plain merge-path", scale=args.scale, relabelled=args.relabelled, ms=r["ms_per_step"], gbs=r["gbs"],
+    emit(what="plain merge-path", dataset=args.dataset, scale=args.scale, relabelled=args.relabelled, ms=r["ms_per_step"], gbs=r["gbs"],
          frac_of_measured_peak=r["gbs"] / peak, frac_of_8000=r["gbs"] / 8000.0)
 
     for cap in [int(c) for c in args.caps.split(",")]:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        plan = sp.CsrPlan(A.ptr, cap)
+        plan = sp.CsrPlan(A.ptr, cap, force=args.dataset != "rmat")
         torch.cuda.synchronize()
         build_ms = (time.perf_counter() - t0) * 1e3
         n_hot, hot_nnz, mode = plan.info()
@@ -72,7 +82,7 @@ def main():
         r = B.bench_kernel(torch, sp, stream, hot, nbytes, args.steps, 3)
         torch.cuda.synchronize()
         same = bool(torch.equal(y0.view(torch.int32), y1.view(torch.int32)))
-        emit(what="hub-column kernel", cap=cap, hot_columns=n_hot, hot_nnz_frac=hot_nnz / max(ci.numel(), 1), mode=mode,
+        emit(what="planned kernel (%s)" % os.environ.get("SPMV_B200_PLAN", "seg"), cap=cap, hot_columns=n_hot, hot_nnz_frac=hot_nnz / max(ci.numel(), 1), mode=mode,
              plan_build_ms=build_ms, ms=r["ms_per_step"], gbs=r["gbs"], frac_of_measured_peak=r["gbs"] / peak,
              frac_of_8000=r["gbs"] / 8000.0, bit_identical_to_plain=same)
         plan.close()

@@ -1,11 +1,14 @@
-"""Hub-column plans (csr_hot_kernels.cu): the persistent merge-path kernel that keeps the x
-entries of the most referenced columns in shared memory.
+"""CSR plans: the planned kernels that keep the x entries of the most referenced columns in shared
+memory -- the segmented-stream kernel (csr_seg_kernels.cu, default) and the hub-column merge-path
+kernel (csr_hot_kernels.cu, SPMV_B200_PLAN=hub).
 
-The plan only changes WHERE x[col] is read from, and the tiles, the per-thread order and the carry
-fix-up are those of the plain merge-path kernel, so every result must be BIT-IDENTICAL to
-spmv_csr(MERGE_PATH) without a plan -- and within the north_star tolerance of the oracle
-(|y - y_ref| <= 1e-5 * sum_j |a_ij x_j| per row against the f64-accumulating restatement of
-spmv_cpu_csr, reference src/spmv_cpu.cpp:6-16)."""
+Every result must be within the north_star tolerance of the oracle (|y - y_ref| <= 1e-5 *
+sum_j |a_ij x_j| per row against the f64-accumulating restatement of spmv_cpu_csr, reference
+src/spmv_cpu.cpp:6-16), deterministic (two products give the same bits), and -- for the
+hub-column merge-path kernel, which only changes WHERE x[col] is read from -- BIT-IDENTICAL to
+spmv_csr(MERGE_PATH) without a plan."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -14,6 +17,8 @@ from gpu_helpers import assert_within_tolerance, bits
 
 pytestmark = pytest.mark.gpu
 MERGE = 2
+SEG = os.environ.get("SPMV_B200_PLAN", "").startswith("s")  # the segmented-stream kernel is forced
+HUB = not SEG  # scale-free inputs (and force=True) get the hub-column merge-path kernel by default
 
 
 def gen_mod():
@@ -40,21 +45,28 @@ def check_plan(sp, orc, dev, rows, cols, rp, ci, va, x, caps, what, expect_mode=
     for cap in caps:
         plan = sp.CsrPlan(A.ptr, cap, force=True)
         n_hot, hot_nnz, mode = plan.info()
-        if expect_mode is not None:
-            assert mode == expect_mode, (what, cap, n_hot, mode)
-        if mode == 1:
-            assert 0 < n_hot <= (cap if cap > 0 else 1 << 20) and 0 < hot_nnz <= len(ci)
+        if expect_mode is not None:  # 1 / 2: hub-column kernel (table / whole x); 3 / 4: segmented stream
+            assert mode == expect_mode + (2 if SEG else 0), (what, cap, n_hot, mode)
+        mode = mode - 2 if mode >= 3 else mode
+        if expect_mode == 1:
+            assert n_hot > 0
+        if mode == 1 and n_hot > 0:
+            assert n_hot <= (cap if cap > 0 else 1 << 20) and 0 < hot_nnz <= len(ci)
             # the admitted columns are the most referenced ones
             counts = np.bincount(ci, minlength=cols)
             order = np.sort(counts)[::-1]
             assert hot_nnz == int(order[:n_hot].sum()), (what, cap, n_hot)
         d_y = torch.full((rows,), float("nan"), dtype=torch.float32, device=dev)
-        for _ in range(2):  # the plan is reusable
-            assert plan.spmv(d_x, d_y) == 0
+        assert plan.spmv(d_x, d_y) == 0
         torch.cuda.synchronize()
         y = d_y.cpu().numpy()
+        d_y.fill_(float("nan"))
+        assert plan.spmv(d_x, d_y) == 0  # the plan is reusable, and the result reproducible
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(y), bits(d_y.cpu().numpy())), f"{what} cap {cap}: two products differ"
         assert_within_tolerance(y, y64, scale, f"{what} cap {cap}")
-        assert np.array_equal(bits(y), bits(y_plain)), f"{what} cap {cap}: differs from plain MERGE_PATH"
+        if HUB:
+            assert np.array_equal(bits(y), bits(y_plain)), f"{what} cap {cap}: differs from plain MERGE_PATH"
         plan.close()
 
 
@@ -67,7 +79,7 @@ def test_rmat_hub_table_matches_plain_merge_path(sp, orc, cuda, scale, ef, seed)
                expect_mode=1)
     # device maximum: at these sizes every column fits -> the table is x itself
     check_plan(sp, orc, cuda, n, n, rp.numpy(), ci.numpy(), va.numpy(), x, caps=(0,), what=f"rmat {scale} all",
-               expect_mode=2 if n <= 49152 else 1)
+               expect_mode=2 if n <= 40000 else 1)
 
 
 @pytest.mark.parametrize("rows,cols,avg,skew,seed", [
@@ -133,7 +145,10 @@ def test_values_are_read_live_and_plan_follows_uploads(sp, orc, cuda):
     y = torch.empty(n, device=cuda)
     assert plan.spmv(x, y) == 0
     y_plain = plain_merge(sp, A, x, n, n)
-    assert np.array_equal(bits(y.cpu().numpy()), bits(y_plain))
+    y64, scale = orc.spmv_csr_f64(n, rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy(), x.cpu().numpy())
+    assert_within_tolerance(y.cpu().numpy(), y64, scale, "new values, old plan")
+    if HUB:
+        assert np.array_equal(bits(y.cpu().numpy()), bits(y_plain))
     plan.close()
 
 
@@ -158,8 +173,9 @@ def test_pagerank_with_and_without_hub_table(sp, orc, cuda):
     for ranks, l2, l1 in outs:
         assert np.abs(ranks.astype(np.float64) - o_ranks).sum() <= 1e-6
         assert abs(l2 - o_l2) <= 1e-8 + 1e-3 * o_l2 and abs(l1 - o_l1) <= 1e-8 + 1e-3 * o_l1
-    for ranks, _, _ in outs[1:]:  # the table changes nothing in the row arithmetic (only the order of the f64 sums)
-        assert np.abs(ranks.astype(np.float64) - outs[0][0]).sum() <= 1e-9
+    for ranks, _, _ in outs[1:]:
+        # hub merge-path: the table changes nothing in the row arithmetic (only the order of the f64 sums)
+        assert np.abs(ranks.astype(np.float64) - outs[0][0]).sum() <= (1e-9 if HUB else 1e-6)
 
 
 def test_spmv_csr_attaches_a_plan_to_csr_to_gpu_uploads(sp, orc, cuda):
@@ -179,10 +195,49 @@ def test_spmv_csr_attaches_a_plan_to_csr_to_gpu_uploads(sp, orc, cuda):
     assert hot_columns > 0 and hot_nnz * 8 >= len(A.ci)
     y3, res = run_csr(sp, A.mat, x, MERGE, cuda, n)
     assert_within_tolerance(y1, y64, scale, "first call")
-    assert np.array_equal(bits(y1), bits(y2)) and np.array_equal(bits(y1), bits(y3))
+    assert_within_tolerance(y2, y64, scale, "second call (planned)")
+    assert np.array_equal(bits(y2), bits(y3))
     assert res.elapsed_ms > 0
     sp.csr_forget_plan(A.mat)
     assert sp.csr_auto_plan_info(A.mat) == (0, 0)
     y4, _ = run_csr(sp, A.mat, x, MERGE, cuda, n)
     assert np.array_equal(bits(y1), bits(y4))
     A.close()
+
+
+def test_plan_kind_follows_the_measured_structure(sp, orc, cuda):
+    """A scale-free matrix gets the hub-column kernel, a regular one with >= 4 non-zeros per row the
+    segmented-stream kernel (no hub worth a table), both through the same CsrPlan call."""
+    if SEG:
+        pytest.skip("SPMV_B200_PLAN forces one kernel")
+    gen = gen_mod()
+    rp, ci, va = gen.laplacian_2d_csr(1500, cuda)
+    n = 1500 * 1500
+    A = sp.DeviceCSR(n, n, rp, ci, va)
+    x = gen.vector_pm1(n, 3, cuda)
+    plan = sp.CsrPlan(A.ptr)
+    assert plan.info()[2] == 3
+    y = torch.full((n,), float("nan"), device=cuda)
+    assert plan.spmv(x, y) == 0
+    torch.cuda.synchronize()
+    y64, scale = orc.spmv_csr_f64(n, rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy(), x.cpu().numpy())
+    assert_within_tolerance(y.cpu().numpy(), y64, scale, "laplacian through the segmented-stream plan")
+    plan.close()
+    n2, rp2, ci2, va2 = gen.rmat_pagerank_csr(19, 16, 5, cuda)
+    A2 = sp.DeviceCSR(n2, n2, rp2, ci2, va2)
+    plan2 = sp.CsrPlan(A2.ptr)
+    assert plan2.info()[2] == 1
+    plan2.close()
+
+
+def test_segmented_stream_kernel_forced(cuda):
+    """The whole file again with SPMV_B200_PLAN=seg (read once per process, hence the subprocess)."""
+    if SEG:
+        pytest.skip("already forced")
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_hot.py"), "-q", "-x", "-m", "gpu"]
+    p = subprocess.run(cmd, env={**os.environ, "SPMV_B200_PLAN": "seg"}, cwd=root, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout[-3000:]
