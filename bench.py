@@ -382,6 +382,13 @@ def run_product_arm(args):
                 dist_on, world)
             extra[f"config2_{name}"] = {"gbs": r["gbs"], "ms": r["ms_per_step"], "frac_of_measured_peak": r["gbs"] / world / peak,
                                         "frac_of_8000": r["gbs"] / world / 8000.0, "bytes": csr_bytes}
+        # the same matrix through a CSR plan: no hub worth a table, >= 4 non-zeros per row -> the
+        # segmented-stream kernel (csr_seg_kernels.cu)
+        plan2 = sp.CsrPlan(A.ptr)
+        r = bench_kernel(torch, sp, stream, lambda: plan2.spmv(x, y, s_ptr), csr_bytes, args.steps, args.warmup, dist_on, world)
+        extra["config2_csr_planned"] = {"gbs": r["gbs"], "ms": r["ms_per_step"], "frac_of_measured_peak": r["gbs"] / world / peak,
+                                        "frac_of_8000": r["gbs"] / world / 8000.0, "bytes": csr_bytes, "plan_mode": plan2.info()[2]}
+        plan2.close()
     sp.ell_destroy(E)
     del A, rp, ci, va, x, y, x_host, y_host
     torch.cuda.empty_cache()
@@ -432,8 +439,8 @@ def run_product_arm(args):
                                             "frac_of_8000": gbs / world / 8000.0, "bytes_all_ranks": float(tot4.item()),
                                             "nnz": n_edges, "rows": n, "scaling": "strong (one graph, row shards)"}
         # the same product through a CSR plan: merge coordinates computed once + hub-column table
-        # (csr_hot_kernels.cu); bit-identical results, checked here on the full-size shard
-        log(f"R-MAT scale {scale}: csr_merge through a hub-column plan")
+        # (csr_hot_kernels.cu) for scale-free shards; bit-identical results, checked here on the full-size shard
+        log(f"R-MAT scale {scale}: csr_merge through a CSR plan")
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         plan = sp.CsrPlan(shard.csr.ptr)

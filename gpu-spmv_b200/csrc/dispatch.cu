@@ -105,7 +105,7 @@ cudaError_t planned_build(const CsrView& A, PlannedCsr* out, int capacity, bool 
     if (kind == 2) return seg_plan_build(A, &out->seg, capacity, force, stream);
     // measured on R-MAT 24 / 26 and the Laplacian (profiles/r1_hub_kernel.md): the hub-column kernel wins
     // on scale-free matrices (and overlaps the PageRank slice exchange), the segmented stream elsewhere
-    cudaError_t e = hot_plan_build(A, &out->hot, capacity, force, stream, kind == 1 ? 8 : 4);
+    cudaError_t e = hot_plan_build(A, &out->hot, capacity, force, stream, 8);
     if (e != cudaSuccess || out->hot.n_hot > 0 || kind == 1 || !allow_seg) return e;
     if (static_cast<long long>(A.nnz) < 4ll * A.rows && !force) return cudaSuccess;
     return seg_plan_build(A, &out->seg, capacity, force, stream);

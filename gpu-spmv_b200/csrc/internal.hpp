@@ -197,7 +197,7 @@ struct PlannedCsr {
     }
 };
 // Chooses by measured structure (SPMV_B200_PLAN=hub|seg forces one): the hub-column plan when
-// its table would serve >= 1/4 of the non-zeros, else -- if allow_seg -- the segmented-stream plan
+// its table would serve >= 1/8 of the non-zeros, else -- if allow_seg -- the segmented-stream plan
 // when rows average >= 4 non-zeros, else nothing (plain merge-path).  Synchronises `stream`.
 cudaError_t planned_build(const CsrView& A, PlannedCsr* out, int capacity, bool force, bool allow_seg,
                           cudaStream_t stream);

@@ -301,7 +301,7 @@ SPMV_B200_API int spmv_b200_csr_normalize_columns_device(spmv_b200_csr* A);
  * everything per call, src/spmv_kernels.cu:258-297).  It holds (1) the merge-path tile
  * coordinates and (2) a PRIVATE re-encoding of col_indices for one of the two planned kernels,
  * chosen by the measured structure: scale-free matrices (a table of the max_hot_columns most
- * referenced columns would serve >= 1/4 of the non-zeros) get the hub-column merge-path kernel of
+ * referenced columns would serve >= 1/8 of the non-zeros) get the hub-column merge-path kernel of
  * csr_hot_kernels.cu, which keeps those x entries in shared memory; other matrices with >= 4
  * non-zeros per row get the segmented-stream kernel of csr_seg_kernels.cu, whose re-encoding also
  * carries the row starts.  The caller's arrays are not modified;
