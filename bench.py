@@ -468,13 +468,21 @@ def run_product_arm(args):
             # fixed number of iterations of the sharded loop (stop rule evaluated every iteration,
             # one iteration late), wall clock around the loop after a device sync, max over ranks
             shard.damping = 0.85
-            modes = (["p2p"] if relabelled else ["p2p", "nccl"]) if dist_on else ["single"]
+            modes = (["multicast", "p2p"] if relabelled else ["multicast", "p2p", "nccl"]) if dist_on else ["single"]
             with torch.cuda.stream(stream):
                 shard.setup_dangling()
+            have_multicast = False
             for mode in modes:
                 log(f"R-MAT scale {scale}: PageRank ({mode})")
                 with torch.cuda.stream(stream):
-                    if mode == "p2p":
+                    if mode == "multicast":
+                        pair = shard.enable_multicast_exchange()
+                        if pair is None:
+                            log("  no NVSwitch multicast on this box / torch build: " + getattr(shard, "_multicast_error", "multicast_ptr == 0"))
+                            continue
+                        have_multicast = True
+                        r_a, r_b = pair
+                    elif mode == "p2p":
                         r_a, r_b = shard.enable_peer_exchange()
                     else:
                         r_a = torch.empty(n, dtype=torch.float32, device=dev)
@@ -499,12 +507,19 @@ def run_product_arm(args):
                     dist.barrier()
                 if mode == "p2p":
                     shard.disable_peer_exchange()
+                if mode == "multicast":
+                    shard.disable_multicast_exchange()
                 it_bytes = float(tot4.item())
-                exchange = {"p2p": "fused into the step kernel: peer stores of finished rows over NVLink (CUDA IPC) "
+                exchange = {"multicast": "fused into the step kernel: ONE NVSwitch-multicast store (multimem.st) per finished "
+                                         "row value, delivered to all GPUs by the switch (torch symmetric memory) "
+                                         "+ NCCL all-reduce of 3 f64",
+                            "p2p": "fused into the step kernel: peer stores of finished rows over NVLink (CUDA IPC) "
                                    "+ NCCL all-reduce of 3 f64",
                             "nccl": "NCCL all-gather of the rank slices + all-reduce of 3 f64",
                             "single": "none (1 GPU)"}[mode]
-                extra[("pagerank" if mode != "nccl" else "pagerank_nccl_allgather") + tag] = {
+                key = {"multicast": "pagerank", "single": "pagerank", "nccl": "pagerank_nccl_allgather",
+                       "p2p": "pagerank_p2p_unicast" if have_multicast else "pagerank"}[mode]
+                extra[key + tag] = {
                     "iters_per_s": iters / sec, "ms_per_iter": sec / iters * 1e3,
                     "graph": f"R-MAT scale {scale} x16, d=0.85" + (", vertex ids relabelled (Graph500-style)" if relabelled
                                                                    else ", no vertex permutation"), "n": n, "nnz": n_edges, "iterations_timed": iters,

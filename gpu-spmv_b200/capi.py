@@ -159,6 +159,7 @@ PROTOTYPES = {
     "spmv_b200_pr_init": (C.c_int, [C.c_int, vp, vp, vp, vp]),
     "spmv_b200_pr_step": (C.c_int, [vp, vp, vp, C.c_float, vp, vp, vp, vp]),
     "spmv_b200_pr_step_p2p": (C.c_int, [vp, vp, vp, C.c_float, vp, vp, vp, C.POINTER(vp), C.c_int, C.c_int, vp]),
+    "spmv_b200_pr_step_multicast": (C.c_int, [vp, vp, vp, C.c_float, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
     "spmv_b200_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), C.c_char_p]),
     "spmv_b200_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
     "spmv_b200_ipc_close": (C.c_int, [vp]),

@@ -442,6 +442,16 @@ int spmv_b200_pr_step_p2p(spmv_b200_pr_plan* plan, const float* d_r_old, float* 
     });
 }
 
+int spmv_b200_pr_step_multicast(spmv_b200_pr_plan* plan, const float* d_r_old, float* d_r_new, float damping,
+                                const float* d_dsum, const uint32_t* d_bits, double* d_partial, float* mc_r_new,
+                                int n_peers, int self_rank, void* stream) {
+    if (!mc_r_new) return kBadArg;
+    return guarded([&] {
+        return b200::pr_step(reinterpret_cast<b200::PrPlan*>(plan), d_r_old, d_r_new, damping, d_dsum, d_bits, d_partial,
+                             static_cast<cudaStream_t>(stream), nullptr, n_peers, self_rank, mc_r_new);
+    });
+}
+
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
 
 int spmv_b200_ipc_alloc(size_t bytes, void** d_ptr, unsigned char handle[64]) {

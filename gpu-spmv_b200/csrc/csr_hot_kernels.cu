@@ -2,15 +2,14 @@
 // CTAs that keep the x entries of the HUB COLUMNS in shared memory.
 //
 // Why.  On a power-law matrix the one-tile-per-CTA merge-path kernel
-// (csr_merge_kernels.cu) is not limited by HBM but by the L1: a scattered 4-byte
-// gather costs one L1 wavefront (one 128-byte line) per lane and an SM retires
-// about one wavefront per clock, i.e. <= 148 x 1.9 GHz = 281 G gathers/s, 0.95 ms
-// for the 268 M non-zeros of R-MAT scale 24 whatever the DRAM bandwidth (ncu:
-// L1TEX 80 %, DRAM 22 %; profiles/r1_ncu_first_path.md).  Shared memory serves
-// 32 random words per clock.  A scale-free matrix concentrates its non-zeros on
-// few columns (R-MAT 24: the 48 K most referenced of 16.7 M columns carry 44 %
-// of the non-zeros), so those x entries are copied ONCE per CTA into a
-// shared-memory table and their gathers never reach the L1.
+// (csr_merge_kernels.cu) is not limited by HBM but by the LSU data pipe of the L1TEX:
+// a scattered 4-byte gather costs one wavefront per distinct 128-byte line and an SM
+// retires one wavefront per clock (ncu on R-MAT 24: data pipe 77 % busy, DRAM 22 %, DRAM
+// traffic = the compulsory bytes; profiles/r1_hub_kernel.md).  A scale-free matrix
+// concentrates its non-zeros on few columns (R-MAT 24: the 24 K most referenced of
+// 16.7 M columns carry 33 % of the non-zeros, the 48 K most referenced 44 %), so those
+// x entries are copied ONCE per CTA into a shared-memory table; a table lookup costs a
+// fraction of a wavefront (1-3 bank-conflict phases per 32 lanes).
 //
 // How.  A column plan (HotPlan), built once per matrix on the device:
 //   1. per-column reference counts (atomics over col_indices),
@@ -22,10 +21,13 @@
 // carry fix-up, same row epilogues as csr_merge_kernels.cu, replacing reference
 // src/spmv_kernels.cu:48-130,267) run by a persistent grid of one 1024-thread
 // CTA per SM.  A CTA = 4 independent 256-thread workers (named barriers), each
-// walking tiles w, w + stride, ...; the 192 KB table is shared by the 4 workers.
-// A worker prefetches the next tile's values / enc span into registers while it
-// reduces the current tile, so the stream latency is off the critical path.
-// When the whole x fits the table (cols <= capacity) no plan is needed.
+// walking tiles w, w + stride, ...; the table is shared by the 4 workers.  A worker
+// loads the next tile's values / enc span into the registers the current tile no longer
+// needs, right before it starts reducing it, so the stream latency is off the critical
+// path.  The table defaults to 24 576 entries (96 KB), NOT the 192 KB that would fit:
+// shared memory is carved out of the L1's 256 KB and the L1's lines track the gather
+// misses in flight (49 K entries: 46 % pipe utilisation, 1.86 ms against 1.04 ms).
+// When the whole x fits the table (cols <= 49 152) no re-encoding is needed.
 //
 // Numerics: products and the per-thread serial order are those of the tile
 // kernel; tiles are identical, so results are bit-identical to MERGE_PATH
@@ -33,7 +35,8 @@
 //
 // Roofline: HBM, algorithmic bytes as for every CSR kernel (8*nnz + 4*(rows+1) +
 // 4*cols + 4*rows, reference src/bandwidth.cpp:34-42); enc replaces col_indices
-// in the stream, so the traffic is unchanged.
+// in the stream, so the traffic is unchanged.  Measured: R-MAT 24 1.04 ms = 2.26 TB/s
+// = 34.5 % of the measured HBM peak (tile kernel: 1.27 ms); the data pipe is 68 % busy.
 #include "merge_rows.cuh"
 
 #include <climits>

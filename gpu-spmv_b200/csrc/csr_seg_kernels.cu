@@ -1,16 +1,16 @@
 // csr_seg_kernels.cu -- planned CSR SpMV as a register-resident segmented reduction
-// ("segmented stream").  The kernel behind CSR plans (spmv_b200_csr_plan, PageRank
-// plans, the automatic plans of spmv_csr(MERGE_PATH)); it replaces the same reference
-// code as the merge-path kernels (src/spmv_kernels.cu:48-130,267) for callers that
-// multiply by the same sparsity pattern more than once.
+// ("segmented stream").  One of the two kernels behind CSR plans (spmv_b200_csr_plan and the
+// automatic plans of spmv_csr(MERGE_PATH)): planned_build() (dispatch.cu) picks it for matrices
+// WITHOUT hub columns and with >= 4 non-zeros per row; scale-free matrices and PageRank shards
+// take the hub-column merge-path kernel (csr_hot_kernels.cu).  It replaces the same reference code
+// as the merge-path kernels (src/spmv_kernels.cu:48-130,267) for callers that multiply by the same
+// sparsity pattern more than once.
 //
-// Why not merge-path here.  ncu on R-MAT 24 (profiles/r1_hub_kernel.md): the merge-path
-// tile kernels sit on the L1TEX DATA PIPE (one wavefront per clock and SM, 68-77 % busy),
-// and only 60 % of those wavefronts are x gathers -- the rest is the algorithm's own
-// shared-memory traffic (products parked in shared memory, a binary search per thread,
-// row ends re-read in the consume loop), plus ~86 thread-instructions per non-zero
-// (issue slots 60 % busy).  A plan may hold a private re-encoding of col_indices, so the
-// row structure can travel WITH the stream instead of being searched for:
+// Idea.  ncu (profiles/r1_hub_kernel.md): the merge-path tile kernels are bound by the L1TEX data
+// pipe, and a third of their wavefronts on it are the algorithm's own shared-memory traffic
+// (products parked in shared memory, a binary search per thread, row ends re-read in the consume
+// loop).  A plan may hold a private re-encoding of col_indices, so the row structure can travel
+// WITH the stream instead of being searched for:
 //
 //   enc[j]  bit 31  the column is a hub: bits 0..29 = slot of the shared-memory x table
 //           bit 30  non-zero j is the FIRST of its row ("head")
@@ -18,21 +18,28 @@
 //   rows_nz[k]          row of the k-th head (rows without non-zeros never appear)
 //   span_head_base[s]   number of heads before non-zero s * 256 (one entry per warp and tile)
 //
-// A tile is 2048 consecutive non-zeros of one 256-thread worker (4 workers per
-// persistent 1024-thread CTA, one CTA per SM, as in csr_hot_kernels.cu).  A lane owns
-// two runs of 4 consecutive non-zeros (two 128-bit loads of values and of enc, fully
-// coalesced), gathers its 8 x entries (hub columns from the table), and reduces its
-// runs serially IN REGISTERS: sums closed inside a run are stored straight to
-// y[rows_nz[.]]; the open ends are combined by a warp-shuffle segmented scan, then
-// across the 8 warps through 32 words of shared memory, then across tiles by a
-// fix-up kernel (tile_lead / tile_tail), always in index order -- deterministic, no
-// atomics.  No search, no products in shared memory, no row_ptrs traffic at all.
-// Rows without non-zeros are never touched: y is zeroed first (plain SpMV) or the
-// PageRank epilogue kernel substitutes 0 (bit mask of non-empty rows).
+// A tile is 2048 consecutive non-zeros of one 256-thread worker (4 workers per persistent
+// 1024-thread CTA, one CTA per SM, as in csr_hot_kernels.cu).  A lane owns two runs of 4
+// consecutive non-zeros (two 128-bit loads of values and of enc, fully coalesced), gathers its 8 x
+// entries (hub columns from the table), and reduces its runs serially IN REGISTERS: sums closed
+// inside a run are stored straight to y[rows_nz[.]]; the open ends are combined by a warp-shuffle
+// segmented scan whose flags come from one ballot (only values are shuffled), then across the 8
+// warps through a few words of shared memory, then across tiles by a fix-up kernel (tile_lead /
+// tile_tail), always in index order -- deterministic, no atomics.  No search, no products in
+// shared memory, no row_ptrs traffic, no merge items for empty rows.  Rows without non-zeros are
+// never touched: y is zeroed first (plain SpMV) or the PageRank epilogue kernel substitutes 0 (bit
+// mask of non-empty rows).  scripts/seg_model.py is an executable model of the index logic.
+//
+// Measured (profiles/r1_hub_kernel.md): Laplacian 4096^2 0.263 ms against 0.382 ms for merge-path
+// (3.3 TB/s, 51 % of the measured HBM peak); R-MAT 24 1.12 ms against 1.04 ms for the hub-column
+// kernel -- warp shuffles occupy the same data pipe as shared-memory accesses, and the instruction
+// count equals merge-path's, so on a gather-bound matrix the shorter critical path of merge-path's
+// 4 overlapping workers wins.  Its PageRank form exchanges the slices in a separate epilogue pass
+// (no overlap with the product), which costs 25 % on 8 GPUs; PageRank plans do not use it.
 //
 // Roofline: HBM; algorithmic bytes as for every CSR kernel (8*nnz + 4*(rows+1) + 4*cols
-// + 4*rows, reference src/bandwidth.cpp:34-42).  The kernel reads 8 B per non-zero +
-// 4 B per non-empty row + x, and writes y.
+// + 4*rows, reference src/bandwidth.cpp:34-42).  The kernel reads 8 B per non-zero + 4 B per
+// non-empty row + 4 B per 256 non-zeros + x, and writes y.
 #include "device_utils.cuh"
 #include "internal.hpp"
 
@@ -336,9 +343,13 @@ seg_pagerank_epilogue_kernel(PageRankStepArgs a, int rows, const uint32_t* __res
         l1 += fabs(diff);
         if ((a.bits[g >> 5] >> (g & 31)) & 1u) dangling += static_cast<double>(v);
         if (a.n_peers > 1) {
+            if (a.mc_r_new) {
+                dev::st_multicast_f(a.mc_r_new + g, v);  // NVSwitch multicast: one store reaches every peer
+            } else {
 #pragma unroll
-            for (int p = 0; p < kMaxPeers; ++p)  // static indices: the pointer table stays in the constant bank
-                if (p < a.n_peers && p != a.self_rank) a.peers[p][g] = v;
+                for (int p = 0; p < kMaxPeers; ++p)  // static indices: the pointer table stays in the constant bank
+                    if (p < a.n_peers && p != a.self_rank) a.peers[p][g] = v;
+            }
         }
     }
     l2 = dev::warp_sum(l2); l1 = dev::warp_sum(l1); dangling = dev::warp_sum(dangling);

@@ -69,6 +69,12 @@ __device__ __forceinline__ void st_stream_f2(float* p, float2 v) {
                  :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
 
+// ---- NVSwitch multicast store (NVLS): one store, delivered to every GPU bound to the multicast
+// object the address belongs to.  SASS: a store to a multicast-mapped address.
+__device__ __forceinline__ void st_multicast_f(float* mc_addr, float v) {
+    asm volatile("multimem.st.weak.global.f32 [%0], %1;" :: "l"(mc_addr), "f"(v) : "memory");
+}
+
 // ---- shared-memory address helper -------------------------------------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -102,6 +102,10 @@ struct PageRankStepArgs {
     float* peers[kMaxPeers];
     int n_peers;
     int self_rank;
+    // NVSwitch multicast address of r_new (NVLS): when set, ONE multimem.st per value reaches the
+    // r_new buffer of every GPU of the group (this one included) instead of n_peers - 1 unicast
+    // stores, so the NVLink egress of a rank is 4 bytes per owned row instead of 4 * (n_peers - 1).
+    float* mc_r_new;
 };
 
 // ---- kernel launchers (stream-ordered; return the launch status) --------------------
@@ -256,7 +260,7 @@ void pr_plan_destroy(PrPlan* plan);
 int pr_plan_set_hot(PrPlan* plan, int max_hot_columns, bool force, cudaStream_t stream);
 int pr_step(PrPlan* plan, const float* d_r_old, float* d_r_new, float damping, const float* d_dsum,
             const uint32_t* d_bits, double* d_partial, cudaStream_t stream,
-            float* const* peer_r_new = nullptr, int n_peers = 0, int self_rank = 0);
+            float* const* peer_r_new = nullptr, int n_peers = 0, int self_rank = 0, float* mc_r_new = nullptr);
 const CsrView& pr_plan_view(const PrPlan* plan);
 double* pr_plan_tmp(PrPlan* plan);
 int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,

@@ -92,6 +92,10 @@ struct PageRankRowT {
         if (!TWO_PASS) {
             if (a.n_peers <= 1) return;
             const volatile float* src = a.r_new;
+            if (a.mc_r_new) {  // NVSwitch multicast: one store reaches every peer
+                for (int g = g0 + tid; g < g1; g += kT) dev::st_multicast_f(a.mc_r_new + g, src[g]);
+                return;
+            }
 #pragma unroll
             for (int p = 0; p < kMaxPeers; ++p) {  // static indices: the pointer table stays in the constant bank
                 if (p >= a.n_peers || p == a.self_rank) continue;
@@ -109,9 +113,13 @@ struct PageRankRowT {
             s.l1 += fabs(diff);
             if ((a.bits[g >> 5] >> (g & 31)) & 1u) s.dangling += static_cast<double>(v);
             if (a.n_peers > 1) {
+                if (a.mc_r_new) {
+                    dev::st_multicast_f(a.mc_r_new + g, v);  // NVSwitch multicast: one store reaches every peer
+                } else {
 #pragma unroll
-                for (int p = 0; p < kMaxPeers; ++p)  // static indices: the pointer table stays in the constant bank
-                    if (p < a.n_peers && p != a.self_rank) a.peers[p][g] = v;
+                    for (int p = 0; p < kMaxPeers; ++p)  // static indices: the pointer table stays in the constant bank
+                        if (p < a.n_peers && p != a.self_rank) a.peers[p][g] = v;
+                }
             }
         }
     }
@@ -124,6 +132,10 @@ struct PageRankRowT {
         if (a.n_peers <= 1) return;
         const int g = a.row_offset + row;
         const float v = a.r_new[g];
+        if (a.mc_r_new) {
+            dev::st_multicast_f(a.mc_r_new + g, v);
+            return;
+        }
 #pragma unroll
         for (int p = 0; p < kMaxPeers; ++p)
             if (p < a.n_peers && p != a.self_rank) a.peers[p][g] = v;

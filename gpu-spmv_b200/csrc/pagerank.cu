@@ -105,15 +105,16 @@ int pr_plan_set_hot(PrPlan* p, int max_hot_columns, bool force, cudaStream_t str
 
 int pr_step(PrPlan* p, const float* d_r_old, float* d_r_new, float damping, const float* d_dsum,
             const uint32_t* d_bits, double* d_partial, cudaStream_t stream, float* const* peer_r_new, int n_peers,
-            int self_rank) {
+            int self_rank, float* mc_r_new) {
     if (!p || !d_r_old || !d_r_new || !d_dsum || !d_bits || !d_partial)
         return static_cast<int>(SpMVError::INVALID_ARGUMENT);
-    if (n_peers > kMaxPeers || (n_peers > 1 && (!peer_r_new || self_rank < 0 || self_rank >= n_peers)))
+    if (n_peers > kMaxPeers || (n_peers > 1 && ((!peer_r_new && !mc_r_new) || self_rank < 0 || self_rank >= n_peers)))
         return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     PageRankStepArgs a;
     a.n_peers = n_peers > 1 ? n_peers : 0;
     a.self_rank = self_rank;
-    for (int i = 0; i < kMaxPeers; ++i) a.peers[i] = (n_peers > 1 && i < n_peers) ? peer_r_new[i] : nullptr;
+    for (int i = 0; i < kMaxPeers; ++i) a.peers[i] = (n_peers > 1 && i < n_peers && peer_r_new) ? peer_r_new[i] : nullptr;
+    a.mc_r_new = n_peers > 1 ? mc_r_new : nullptr;
     a.r_old = d_r_old;
     a.r_new = d_r_new;
     a.row_offset = p->row_offset;

@@ -182,6 +182,7 @@ class CudaShard:
         self.dsum = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.damping = 0.85
         self._peer_tables, self._world, self._rank = {}, 1, 0
+        self._multicast, self._symm = {}, []
 
     def _s(self):
         return C.c_void_p(self.stream if self.stream is not None else torch.cuda.current_stream().cuda_stream)
@@ -214,6 +215,14 @@ class CudaShard:
         assert rc == 0
 
     def __call__(self, r_old, r_new, partial):
+        mc = self._multicast.get(r_new.data_ptr()) if self._multicast else None
+        if mc is not None:  # slice exchange fused into the step, one NVSwitch-multicast store per value
+            rc = sp.lib.spmv_b200_pr_step_multicast(self.plan, sp.dptr(r_old), sp.dptr(r_new), self.damping,
+                                                    sp.dptr(self.dsum), sp.dptr(self.bits), sp.dptr(partial),
+                                                    C.c_void_p(mc), self._world, self._rank, self._s())
+            if rc != 0:
+                raise RuntimeError(f"pr_step_multicast: {sp.spmv_error_string(rc)}")
+            return
         table = self._peer_tables.get(r_new.data_ptr()) if self._peer_tables else None
         if table is not None:  # slice exchange fused into the step (peer stores over NVLink)
             rc = sp.lib.spmv_b200_pr_step_p2p(self.plan, sp.dptr(r_old), sp.dptr(r_new), self.damping,
@@ -229,7 +238,35 @@ class CudaShard:
     @property
     def delivers_slices(self):
         """True when the step itself writes this rank's slice into every peer's vector."""
-        return bool(self._peer_tables)
+        return bool(self._peer_tables) or bool(self._multicast)
+
+    def enable_multicast_exchange(self, group=None):
+        """The two rank-vector buffers as torch symmetric memory bound to an NVSwitch multicast
+        object: the step then sends every finished value ONCE (multimem.st) and the switch delivers
+        it to all GPUs.  torch.distributed._symmetric_memory does the plumbing (cuMem allocation,
+        handle exchange, cuMulticast* binding); returns (r_a, r_b) or None when the box / torch
+        build has no multicast support (callers then fall back to enable_peer_exchange)."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            self._world, self._rank = dist.get_world_size(group), dist.get_rank(group)
+            pg = group if group is not None else dist.group.WORLD
+            bufs, handles = [], []
+            for _ in range(2):
+                t = symm_mem.empty(self.n, dtype=torch.float32, device=self.dev)
+                h = symm_mem.rendezvous(t, pg)
+                if not getattr(h, "multicast_ptr", 0):
+                    return None
+                bufs.append(t)
+                handles.append(h)
+        except Exception as exc:  # no symmetric memory in this build / on this box
+            self._multicast_error = repr(exc)
+            return None
+        self._symm = handles  # keep the mappings alive
+        self._multicast = {t.data_ptr(): int(h.multicast_ptr) for t, h in zip(bufs, handles)}
+        return tuple(bufs)
+
+    def disable_multicast_exchange(self):
+        self._multicast, self._symm = {}, []
 
     def enable_peer_exchange(self, group=None):
         """Allocates the two rank-vector buffers of the iteration as CUDA-IPC shareable memory,
@@ -291,10 +328,15 @@ def pagerank_sharded(shard, bounds, damping=0.85, tolerance=1e-6, max_iterations
                      fixed_iterations=0, fused_exchange=False):
     """PageRank over row shards, one CudaShard per rank; returns a PageRankOutcome whose
     ranks tensor (full length, normalised) is identical on every rank.  fused_exchange=True
-    replaces the NCCL all-gather by peer stores from inside the step kernel."""
+    replaces the NCCL all-gather by peer stores from inside the step kernel; "multicast" by one
+    NVSwitch-multicast store per value (falls back to peer stores when the box has no multicast)."""
     shard.damping = float(damping)
     shard.setup_dangling(group)
-    if fused_exchange and dist.is_initialized() and dist.get_world_size(group) > 1:
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    pair = shard.enable_multicast_exchange(group) if (fused_exchange == "multicast" and multi) else None
+    if pair is not None:
+        r_a, r_b = pair
+    elif fused_exchange and multi:
         r_a, r_b = shard.enable_peer_exchange(group)
     else:
         r_a = torch.empty(shard.n, dtype=torch.float32, device=shard.dev)

@@ -384,6 +384,19 @@ SPMV_B200_API int spmv_b200_pr_step_p2p(spmv_b200_pr_plan* plan, const float* d_
                                         double* d_partial, float* const* peer_r_new, int n_peers,
                                         int self_rank, void* stream);
 
+/*
+ * The same fused exchange through NVSwitch multicast (NVLS): mc_r_new is the MULTICAST address of
+ * the r_new buffers of all n_peers ranks (every rank's buffer bound at the same offset of one
+ * multicast object, e.g. torch.distributed._symmetric_memory's multicast_ptr); each finished rank
+ * value is sent ONCE (multimem.st) and the switch delivers it to every GPU, so a rank's NVLink
+ * egress is 4 bytes per owned row instead of 4 * (n_peers - 1).  d_r_new is this rank's own
+ * (unicast) mapping of its buffer.  Ordering rule as for spmv_b200_pr_step_p2p.
+ */
+SPMV_B200_API int spmv_b200_pr_step_multicast(spmv_b200_pr_plan* plan, const float* d_r_old,
+                                              float* d_r_new, float damping, const float* d_dsum,
+                                              const uint32_t* d_bits, double* d_partial,
+                                              float* mc_r_new, int n_peers, int self_rank, void* stream);
+
 /* Device buffers that other processes of the box can map (CUDA IPC): alloc returns the device
  * pointer and a 64-byte handle to send to the peers; open maps a peer's handle. */
 SPMV_B200_API int spmv_b200_ipc_alloc(size_t bytes, void** d_ptr, unsigned char handle[64]);

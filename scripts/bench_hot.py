@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Tuning aid: plain merge-path vs the hub-column kernel (csr_hot_kernels.cu) on an R-MAT graph.
+"""Tuning aid: plain merge-path vs the planned kernels (csr_hot_kernels.cu, csr_seg_kernels.cu).
 
     python scripts/bench_hot.py --scale 24 --caps 0,32768,16384,4096 [--pagerank] [--relabelled]
+    SPMV_B200_PLAN=seg python scripts/bench_hot.py --dataset c2 --caps 0
 
 Prints one JSON line per measurement (CUDA events on the launching stream, after warm-up)."""
 import argparse

@@ -1,6 +1,7 @@
 """Sharded PageRank on >= 2 GPUs of one box (one process per GPU, NCCL): the NCCL all-gather
-path and the fused peer-store exchange must both reproduce the single-GPU result, and must be
-bitwise identical to each other (same kernels, same summation order, only the transport differs).
+path, the fused peer-store exchange and the fused NVSwitch-multicast exchange must all reproduce
+the single-GPU result, and must be bitwise identical to each other (same kernels, same summation
+order, only the transport differs).
 Skipped on boxes with a single GPU."""
 import os
 import socket
@@ -43,17 +44,25 @@ def _worker(rank, world, port, scale, out_dir):
         srp, sci, sva = D.extract_shard(rp, ci, va, bounds[rank], bounds[rank + 1])
         torch.cuda.synchronize()
         results = {}
-        for mode in ("nccl", "p2p"):
+        used_multicast = False
+        for mode in ("nccl", "p2p", "multicast"):
             shard = D.CudaShard(n, bounds[rank], srp, sci, sva)
-            out = D.pagerank_sharded(shard, bounds, 0.85, 1e-6, 100, fused_exchange=(mode == "p2p"))
+            out = D.pagerank_sharded(shard, bounds, 0.85, 1e-6, 100,
+                                     fused_exchange={"nccl": False, "p2p": True, "multicast": "multicast"}[mode])
             torch.cuda.synchronize()
             results[mode] = (out.ranks.clone(), out.iterations, out.final_residual, out.converged)
+            if mode == "multicast":
+                used_multicast = bool(shard._multicast)  # False: no NVSwitch multicast here, peer stores were used
             dist.barrier()
             shard.disable_peer_exchange()
+            shard.disable_multicast_exchange()
             shard.close()
-        a, b = results["nccl"], results["p2p"]
-        assert a[1:] == b[1:], (a[1:], b[1:])
+        a, b, c = results["nccl"], results["p2p"], results["multicast"]
+        assert a[1:] == b[1:] == c[1:], (a[1:], b[1:], c[1:])
         assert torch.equal(a[0], b[0]), "fused peer-store exchange differs from the NCCL all-gather path"
+        assert torch.equal(a[0], c[0]), "multicast exchange differs from the NCCL all-gather path"
+        if rank == 0:
+            print(f"multicast exchange exercised: {used_multicast}")
         np.save(os.path.join(out_dir, f"ranks_{rank}.npy"), a[0].cpu().numpy())
         np.save(os.path.join(out_dir, f"meta_{rank}.npy"), np.array([a[1], a[2], float(a[3])]))
     finally:
