@@ -416,9 +416,10 @@ def run_product_arm(args):
     def rmat_section(scale, seed, do_vector, do_pagerank, relabelled=False):
         log(f"R-MAT scale {scale}: build" + (" (relabelled vertices)" if relabelled else ""))
         tag = "_relabelled" if relabelled else ""
-        # SpMV shards balance the merge items (rows + nnz); PageRank shards also pay 4 bytes per
-        # owned row to every peer, so rows weigh more there (tuned on 8 GPUs, profiles/)
-        weight = args.row_weight if args.row_weight >= 0 else (1 if not do_pagerank or world == 1 or relabelled else 8)
+        # SpMV shards balance the merge items (rows + nnz); a PageRank shard also updates and sends
+        # every owned row, so rows weigh more there (8 GPUs, multicast exchange: weight 1 / 4 ->
+        # 995 / 1063 iter/s; with unicast peer stores 8 was best, profiles/)
+        weight = args.row_weight if args.row_weight >= 0 else (1 if not do_pagerank or world == 1 or relabelled else 4)
         n, bounds, srp, sci, sva, n_edges = build_rmat_shard(torch, gen, scale, 16, seed, rank, world, dev,
                                                             row_weight=weight, relabelled=relabelled)
         torch.cuda.synchronize()
