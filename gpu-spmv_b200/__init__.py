@@ -13,6 +13,7 @@ has not been built, and device calls fail if no B200 is present.
 """
 import ctypes as C
 import enum
+import os
 
 import numpy as np
 
@@ -367,6 +368,18 @@ def pagerank_top_k(ranks, k):
             np.array([out[i].rank for i in range(kk)], dtype=np.float32))
 
 
+def pagerank_top_k_device(d_ranks, k):
+    """Top-k of a DEVICE rank vector (torch float32) -> (node ids, ranks), rank descending, id ascending on ties."""
+    n = int(d_ranks.numel())
+    kk = min(k, n)
+    out = (TopKNode * max(kk, 1))()
+    rc = lib.spmv_b200_pagerank_top_k_device(dptr(d_ranks), n, int(k), out)
+    if rc != 0:
+        raise RuntimeError(f"pagerank_top_k_device: {spmv_error_string(rc)}")
+    return (np.array([out[i].node_id for i in range(kk)], dtype=np.int32),
+            np.array([out[i].rank for i in range(kk)], dtype=np.float32))
+
+
 def pagerank_device(adj_matrix, d_ranks, config=None):
     """Whole loop on the device; d_ranks (torch float32 [n]) receives the ranks."""
     it, res, conv, l1 = C.c_int(0), C.c_float(0), C.c_bool(False), C.c_double(0)
@@ -432,6 +445,14 @@ def benchmark_from_json(text):
 
 def launch_count():
     return int(lib.spmv_b200_launch_count())
+
+
+def csr_load_matrix_market(mat, filename):
+    return lib.spmv_b200_csr_load_matrix_market(mat, os.fsencode(filename))
+
+
+def csr_save_matrix_market(mat, filename):
+    return lib.spmv_b200_csr_save_matrix_market(mat, os.fsencode(filename))
 
 
 def csr_from_coo_device(out, rows, cols, d_rows, d_cols, d_vals):

@@ -143,6 +143,9 @@ PROTOTYPES = {
     "spmv_b200_merge_path_search": (C.c_int, [C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p]),
     "spmv_b200_partition_rows": (C.c_int, [c_int_p, C.c_int, C.c_int, c_int_p]),
     "spmv_b200_partition_rows_weighted": (C.c_int, [c_int_p, C.c_int, C.c_int, C.c_int, c_int_p]),
+    "spmv_b200_pagerank_top_k_device": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(TopKNode)]),
+    "spmv_b200_csr_load_matrix_market": (C.c_int, [CSR_P, C.c_char_p]),
+    "spmv_b200_csr_save_matrix_market": (C.c_int, [CSR_P, C.c_char_p]),
     "spmv_b200_csr_from_coo_device": (C.c_int, [CSR_P, C.c_int, C.c_int, C.c_longlong, vp, vp, vp]),
     "spmv_b200_csr_normalize_columns_device": (C.c_int, [CSR_P]),
     "spmv_b200_csr_plan_create": (C.c_int, [CSR_P, C.c_int, C.c_int, C.POINTER(vp)]),

@@ -352,6 +352,19 @@ int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, int parts, int* 
     return spmv_b200_partition_rows_weighted(row_ptrs, num_rows, parts, 0, bounds);
 }
 
+int spmv_b200_pagerank_top_k_device(const float* d_ranks, int num_nodes, int k, spmv_b200_topk_node* top_k) {
+    return guarded([&] {
+        return b200::pagerank_top_k_device(d_ranks, num_nodes, k, reinterpret_cast<TopKNode*>(top_k));
+    });
+}
+
+int spmv_b200_csr_load_matrix_market(spmv_b200_csr* out, const char* filename) {
+    return guarded([&] { return b200::csr_load_matrix_market(cpp(out), filename); });
+}
+int spmv_b200_csr_save_matrix_market(const spmv_b200_csr* m, const char* filename) {
+    return guarded([&] { return b200::csr_save_matrix_market(cpp(m), filename); });
+}
+
 int spmv_b200_csr_from_coo_device(spmv_b200_csr* out, int rows, int cols, long long n_entries, const int* d_row_indices,
                                   const int* d_col_indices, const float* d_values) {
     return guarded([&] {

@@ -651,9 +651,16 @@ cudaError_t launch_csr_warp_per_row(const CsrView& A, const float* x, float* y, 
 }
 
 // lanes per row for VECTOR_CSR from the average row length:
-// <8 -> 2, <16 -> 4, <32 -> 8, <64 -> 16, else a full warp
+// <6 -> 1, <8 -> 2, <16 -> 4, <32 -> 8, <64 -> 16, else a full warp.
+// One lane per row IS the row-owner pipeline of SCALAR_CSR (sequential order): on rows this short
+// sharing a row between lanes only adds shuffles -- config 2 (5 per row): 0.165 ms against 0.183 ms
+// with two lanes.  The selector only sends matrices with max <= 10 * (min + 1) here, so no lane is
+// left alone with a long row.  SPMV_B200_VECTOR_LANES forces a width (A/B timing).
 int vector_lanes_for(int rows, int nnz) {
+    static const int forced = stream_env_int("SPMV_B200_VECTOR_LANES", 0);
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
     const double avg = rows > 0 ? static_cast<double>(nnz) / rows : 0.0;
+    if (avg < 6.0) return 1;
     if (avg < 8.0) return 2;
     if (avg < 16.0) return 4;
     if (avg < 32.0) return 8;

@@ -231,6 +231,13 @@ int csr_from_coo_device(CSRMatrix* out, int rows, int cols, long long n_entries,
 // matrix pagerank() expects (reference include/spmv/pagerank.h:28)
 int csr_normalize_columns_device(CSRMatrix* A);
 
+// ---- device top-k of a rank vector in HBM (topk.cu); top_k is a host array of min(k, n) entries ----
+int pagerank_top_k_device(const float* d_ranks, int n, int k, TopKNode* top_k);
+
+// ---- Matrix Market coordinate files (matrix_market.cpp; host arrays only) -----------------
+int csr_load_matrix_market(CSRMatrix* out, const char* filename);
+int csr_save_matrix_market(const CSRMatrix* m, const char* filename);
+
 // ---- stream-ordered dispatch used by the blocking API, benchmark and PageRank --------
 // Chooses and launches the kernel(s) for `kernel_type` (any unknown value ->
 // SCALAR, as src/spmv_kernels.cu:287-288).  `scratch` backs merge-path plans.

@@ -279,6 +279,27 @@ SPMV_B200_API int spmv_b200_partition_rows(const int* row_ptrs, int num_rows, in
 SPMV_B200_API int spmv_b200_partition_rows_weighted(const int* row_ptrs, int num_rows, int parts,
                                                     int row_weight, int* bounds /* [parts+1] */);
 
+/* ---- device top-k ---------------------------------------- */
+
+/* Top-k of a rank vector that is already in device memory (e.g. spmv_b200_pagerank_device's
+ * d_ranks): radix select + ordered tie fill on the device, only min(k, n) pairs are downloaded.
+ * Same values as pagerank_top_k (src/pagerank.cu:162-185, which sorts a host copy of all n
+ * pairs); equal ranks are ordered by ascending node id (the reference leaves ties unordered). */
+SPMV_B200_API int spmv_b200_pagerank_top_k_device(const float* d_ranks, int num_nodes, int k,
+                                                  spmv_b200_topk_node* top_k);
+
+/* ---- Matrix Market input ------------------------------- */
+
+/* `%%MatrixMarket matrix coordinate {real|integer|pattern} {general|symmetric|skew-symmetric}`
+ * -> host arrays of `out` (re-allocated and owned, sorted by (row, column), symmetric files
+ * expanded, pattern entries = 1, duplicates kept in file order; device arrays untouched, as
+ * csr_from_dense, src/csr_matrix.cpp:50-95).  The reference lists real-matrix input as a
+ * requirement but has no loader.  Unreadable file -> FILE_IO; anything else unsupported or
+ * malformed -> INVALID_FORMAT with `out` unchanged. */
+SPMV_B200_API int spmv_b200_csr_load_matrix_market(spmv_b200_csr* out, const char* filename);
+/* coordinate real general, CSR order, values with 9 significant digits (exact for fp32) */
+SPMV_B200_API int spmv_b200_csr_save_matrix_market(const spmv_b200_csr* m, const char* filename);
+
 /* ---- device-side assembly ------------------------------ */
 
 /* (row, col, value) triplets in DEVICE memory -> CSR sorted by (row, col) in the device arrays of

@@ -202,3 +202,28 @@ def test_reference_cuda_pagerank_agrees(sp, orc, ref, cuda):
     ref.L.ref_pagerank_top_k(ranks.ctypes.data_as(C.POINTER(C.c_float)), n, 10, rid.ctypes.data_as(C.POINTER(C.c_int)),
                              rv.ctypes.data_as(C.POINTER(C.c_float)))
     assert np.array_equal(vals, rv)  # same ranks position by position (ids may differ only on ties)
+
+
+@pytest.mark.parametrize("n,k,kind", [(1, 1, "rand"), (10, 20, "rand"), (5000, 7, "rand"), (300000, 100, "rand"),
+                                      (300000, 1000, "ties"), (70000, 50, "const"), (100003, 10, "neg")])
+def test_device_top_k_matches_host_top_k(sp, cuda, n, k, kind):
+    """spmv_b200_pagerank_top_k_device against the API's host pagerank_top_k (src/pagerank.cu:162-185):
+    identical rank values position by position; node ids identical wherever ranks are distinct, and
+    ascending inside a run of equal ranks (the reference leaves ties unordered)."""
+    rng = np.random.default_rng(n + k)
+    if kind == "rand":
+        v = rng.random(n).astype(np.float32)
+    elif kind == "ties":   # few distinct values: the threshold falls inside a long run of equal ranks
+        v = (rng.integers(0, 12, n) / 16.0).astype(np.float32)
+    elif kind == "const":
+        v = np.full(n, 1.0 / n, np.float32)
+    else:                  # negative values and zeros order correctly too
+        v = rng.uniform(-1, 1, n).astype(np.float32)
+        v[::7] = 0.0
+    ids, vals = sp.pagerank_top_k_device(torch.as_tensor(v).to(cuda), k)
+    h_ids, h_vals = sp.pagerank_top_k(v, k)
+    kk = min(k, n)
+    assert len(ids) == kk and np.array_equal(vals, h_vals)
+    assert np.array_equal(v[ids], vals) and len(set(ids.tolist())) == kk
+    expect = np.lexsort((np.arange(n), -v.astype(np.float64)))[:kk]  # rank descending, id ascending
+    assert np.array_equal(ids, expect.astype(np.int32))
