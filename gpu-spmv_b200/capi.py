@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libspmv_b200.so")
+# SPMV_B200_LIB: another build of the same library (A/B timing of build-time constants)
+LIB_PATH = os.environ.get("SPMV_B200_LIB") or os.path.join(_HERE, "lib", "libspmv_b200.so")
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int)

@@ -241,3 +241,40 @@ def test_segmented_stream_kernel_forced(cuda):
     p = subprocess.run(cmd, env={**os.environ, "SPMV_B200_PLAN": "seg"}, cwd=root, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True)
     assert p.returncode == 0, p.stdout[-3000:]
+
+
+def test_full_size_rmat24_properties(sp, cuda):
+    """BASELINE config 4 at full size (R-MAT scale 24, 268 M non-zeros), size-independent properties.
+    The f64 oracle is too slow here, so the checks are relative to SCALAR_CSR (sequential per-row
+    order == spmv_cpu_csr, proven bit-exact at oracle sizes in test_gpu_spmv.py) with the north_star
+    row scale sum_j |a_ij x_j| computed by a product over |A|, |x|:
+      * MERGE_PATH and both planned kernels within 1e-5 * scale of it, row by row;
+      * the hub-column plan BIT-IDENTICAL to MERGE_PATH (only the source of x[col] changes);
+      * linearity A(2x) = 2 A x exactly for every kernel (power-of-two scaling is exact in fp32);
+      * rows without non-zeros are exactly 0."""
+    gen = gen_mod()
+    n, rp, ci, va = gen.rmat_pagerank_csr(24, 16, 44, cuda)
+    assert ci.numel() == 268435456
+    A = sp.DeviceCSR(n, n, rp, ci, va)
+    x = gen.vector_pm1(n, 11, cuda)
+    y_sc, y_mg, y_p, scale = (torch.empty(n, device=cuda) for _ in range(4))
+    assert sp.spmv_csr(A.ptr, x, y_sc, sp.make_config(sp.SCALAR_CSR), n).error_code == 0
+    assert sp.spmv_csr(A.ptr, x, y_mg, sp.make_config(sp.MERGE_PATH), n).error_code == 0
+    absA = sp.DeviceCSR(n, n, rp, ci, va.abs())
+    assert sp.spmv_csr(absA.ptr, x.abs(), scale, sp.make_config(sp.SCALAR_CSR), n).error_code == 0
+    assert bool(((y_mg - y_sc).abs() <= 1e-5 * scale).all())
+    empty = (rp[1:] == rp[:-1])
+    assert int(empty.sum()) > 0 and bool((y_mg[empty] == 0).all())
+    plan = sp.CsrPlan(A.ptr)  # scale-free: the hub-column kernel (the segmented stream under SPMV_B200_PLAN=seg)
+    assert plan.info()[2] == (3 if SEG else 1) and plan.info()[0] > 0
+    y_p.fill_(float("nan"))
+    assert plan.spmv(x, y_p) == 0
+    torch.cuda.synchronize()
+    assert bool(((y_p - y_sc).abs() <= 1e-5 * scale).all()) and bool((y_p[empty] == 0).all())
+    if not SEG:
+        assert torch.equal(y_p.view(torch.int32), y_mg.view(torch.int32))
+    y2 = torch.empty(n, device=cuda)
+    assert plan.spmv(x * 2, y2) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y_p * 2)
+    plan.close()
