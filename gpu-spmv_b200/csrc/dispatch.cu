@@ -98,16 +98,21 @@ static int plan_kind_env() {
 }
 
 cudaError_t planned_build(const CsrView& A, PlannedCsr* out, int capacity, bool force, bool allow_seg,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, bool prefer_seg) {
     out->release();
     if (A.rows <= 0 || A.nnz <= 0) return cudaSuccess;
     const int kind = plan_kind_env();
     if (kind == 2) return seg_plan_build(A, &out->seg, capacity, force, stream);
+    const bool long_enough = static_cast<long long>(A.nnz) >= 4ll * A.rows;
+    if (prefer_seg && kind == 0 && long_enough) {
+        const cudaError_t e = seg_plan_build(A, &out->seg, capacity, force, stream);
+        if (e != cudaSuccess || out->seg.valid()) return e;
+    }
     // measured on R-MAT 24 / 26 and the Laplacian (profiles/r1_hub_kernel.md): the hub-column kernel wins
     // on scale-free matrices (and overlaps the PageRank slice exchange), the segmented stream elsewhere
     cudaError_t e = hot_plan_build(A, &out->hot, capacity, force, stream, 8);
     if (e != cudaSuccess || out->hot.n_hot > 0 || kind == 1 || !allow_seg) return e;
-    if (static_cast<long long>(A.nnz) < 4ll * A.rows && !force) return cudaSuccess;
+    if (!long_enough && !force) return cudaSuccess;
     return seg_plan_build(A, &out->seg, capacity, force, stream);
 }
 

@@ -203,8 +203,9 @@ struct PlannedCsr {
 // Chooses by measured structure (SPMV_B200_PLAN=hub|seg forces one): the hub-column plan when
 // its table would serve >= 1/8 of the non-zeros, else -- if allow_seg -- the segmented-stream plan
 // when rows average >= 4 non-zeros, else nothing (plain merge-path).  Synchronises `stream`.
+// prefer_seg: take the segmented stream first when rows average >= 4 non-zeros (single-shard PageRank).
 cudaError_t planned_build(const CsrView& A, PlannedCsr* out, int capacity, bool force, bool allow_seg,
-                          cudaStream_t stream);
+                          cudaStream_t stream, bool prefer_seg = false);
 // out[3] = ordered sum of `count` triples of per-CTA partial sums
 cudaError_t launch_reduce_partials(const double* partials, int count, double* out, cudaStream_t stream);
 

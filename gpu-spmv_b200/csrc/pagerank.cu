@@ -39,10 +39,13 @@ struct PrPlan {
     MergePlan merge;
     Scratch tmp_block;   // kTmpDoubles doubles
     double* tmp = nullptr;
-    // Hub-column plan of the shard when it is scale-free (the tile epilogue of that kernel also
-    // overlaps the slice exchange with the product: 1.17 vs 1.46 ms per iteration on 8 GPUs against
-    // the segmented-stream kernel, whose exchange is a separate pass); neither: plain tile kernel.
+    // A ROW SHARD of a scale-free graph takes the hub-column plan: the tile epilogue of that kernel
+    // overlaps the slice exchange with the product (8 GPUs, R-MAT 26: 1.17 vs 1.46 ms per iteration
+    // against the segmented-stream kernel, whose exchange is a separate pass).  The WHOLE graph on
+    // one GPU has nothing to exchange and takes the segmented stream with its streaming epilogue
+    // (R-MAT 26: 5.45 vs 5.89 ms per iteration; R-MAT 24: 1.21 vs 1.29).  Neither: plain tile kernel.
     PlannedCsr planned;
+    bool whole_graph = false;
     ~PrPlan() { planned.release(); }
 };
 
@@ -78,7 +81,9 @@ int pr_plan_create(const CSRMatrix* shard, int row_offset, int n_global, cudaStr
         return static_cast<int>(SpMVError::KERNEL_LAUNCH);
     }
     // the matrix is constant over the iterations: the hub-column plan pays for itself after a few
-    if (pr_hot_env() != 0 && planned_build(p->A, &p->planned, 0, pr_hot_env() > 0, false, stream) != cudaSuccess) {
+    p->whole_graph = row_offset == 0 && shard->num_rows == n_global;
+    if (pr_hot_env() != 0 &&
+        planned_build(p->A, &p->planned, 0, pr_hot_env() > 0, p->whole_graph, stream, p->whole_graph) != cudaSuccess) {
         cudaGetLastError();
         p->planned.release();  // not fatal: the plain tile kernel is used
     }
@@ -95,7 +100,8 @@ int pr_plan_set_hot(PrPlan* p, int max_hot_columns, bool force, cudaStream_t str
     cudaStreamSynchronize(stream);
     p->planned.release();
     if (max_hot_columns == 0) return 0;
-    if (planned_build(p->A, &p->planned, max_hot_columns < 0 ? 0 : max_hot_columns, force, false, stream) != cudaSuccess) {
+    if (planned_build(p->A, &p->planned, max_hot_columns < 0 ? 0 : max_hot_columns, force, p->whole_graph, stream,
+                      p->whole_graph) != cudaSuccess) {
         cudaGetLastError();
         p->planned.release();
         return static_cast<int>(SpMVError::CUDA_MALLOC);

@@ -152,10 +152,12 @@ def test_values_are_read_live_and_plan_follows_uploads(sp, orc, cuda):
     plan.close()
 
 
-def test_pagerank_with_and_without_hub_table(sp, orc, cuda):
-    """The fused PageRank iteration through the hub-table kernel: same ranks (L1 <= 1e-6 against
-    the f64 restatement of the reference recurrence, src/pagerank.cu:93-150) and the same residuals
-    as through the plain tile kernel."""
+def test_pagerank_with_and_without_a_plan(sp, orc, cuda):
+    """The fused PageRank iteration through the planned kernels: same ranks (L1 <= 1e-6 against the
+    f64 restatement of the reference recurrence, src/pagerank.cu:93-150) and the same residuals as
+    through the plain tile kernel.  The whole graph on one GPU takes the segmented stream (different,
+    fixed summation order); a ROW SHARD takes the hub-column kernel, whose r_new slice must equal the
+    plain tile kernel's bit for bit (only the source of x[col] changes)."""
     gen = gen_mod()
     import gpu_spmv_b200.dist as D
     n, rp, ci, va = gen.rmat_pagerank_csr(16, 16, 11, cuda)
@@ -174,8 +176,32 @@ def test_pagerank_with_and_without_hub_table(sp, orc, cuda):
         assert np.abs(ranks.astype(np.float64) - o_ranks).sum() <= 1e-6
         assert abs(l2 - o_l2) <= 1e-8 + 1e-3 * o_l2 and abs(l1 - o_l1) <= 1e-8 + 1e-3 * o_l1
     for ranks, _, _ in outs[1:]:
-        # hub merge-path: the table changes nothing in the row arithmetic (only the order of the f64 sums)
-        assert np.abs(ranks.astype(np.float64) - outs[0][0]).sum() <= (1e-9 if HUB else 1e-6)
+        assert np.abs(ranks.astype(np.float64) - outs[0][0]).sum() <= 1e-6
+
+    # one step on a row shard (rows [lo, hi) of the graph): hub-column kernel against the plain tile kernel
+    lo, hi = n // 5, (3 * n) // 4
+    srp, sci, sva = D.extract_shard(rp, ci, va, lo, hi)
+    shard = D.CudaShard(n, lo, srp, sci, sva)
+    shard.setup_dangling()
+    r_old = torch.empty(n, device=cuda)
+    shard.init_vector(r_old)
+    r_old.mul_(gen.vector_pm1(n, 2, cuda).abs() + 0.5)  # not the uniform start vector
+    slices, partials = [], []
+    for cap in (0, 300):
+        used = shard.set_hot(cap, force=True)
+        assert (used == 0) == (cap == 0)
+        r_new = torch.full((n,), float("nan"), device=cuda)
+        partial = torch.zeros(3, dtype=torch.float64, device=cuda)
+        shard(r_old, r_new, partial)
+        torch.cuda.synchronize()
+        assert bool(torch.isnan(r_new[:lo]).all()) and bool(torch.isnan(r_new[hi:]).all())  # only the shard's rows
+        slices.append(r_new[lo:hi].clone())
+        partials.append(partial.cpu().numpy())
+    if not SEG:
+        assert torch.equal(slices[0].view(torch.int32), slices[1].view(torch.int32))
+    assert float((slices[0] - slices[1]).abs().sum()) <= 1e-6
+    assert np.allclose(partials[0], partials[1], rtol=1e-4 if SEG else 1e-9, atol=1e-18)
+    shard.close()
 
 
 def test_spmv_csr_attaches_a_plan_to_csr_to_gpu_uploads(sp, orc, cuda):
