@@ -547,7 +547,10 @@ def run_product_arm(args):
         roofline = {"bound": "hbm", "achieved": launch_gbs, "peak": peak, "unit": "GB/s", "frac": launch_gbs / peak,
                     "peak_source": peak_src, "frac_of_8000_nominal": launch_gbs / 8000.0,
                     "kernel": "ell_tma_pipe_kernel<1>", "algorithmic_bytes_per_launch": ell_bytes,
-                    "traffic": args.ncu_traffic}
+                    # dram__bytes_read.sum + dram__bytes_write.sum of ell_tma_pipe_kernel<1> on this workload, one
+                    # `ncu --set full` capture (profiles/r1_ell_tma_pipe_c2_raw.csv: 738.8 + 61.9 MB; y is
+                    # partly still in L2 at kernel end, hence slightly below the 805.3 MB algorithmic)
+                    "traffic": args.ncu_traffic if args.ncu_traffic is not None else (800728576.0 if world == 1 else None)}
         line = {
             "metric": "spmv_effective_hbm_gbs", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -581,7 +584,8 @@ def main():
     ap.add_argument("--relabelled", type=int, default=1,
                     help="also run PageRank on the same R-MAT graph with relabelled vertex ids (extra.pagerank_relabelled)")
     ap.add_argument("--ncu-traffic", type=float, default=None,
-                    help="dram bytes per launch of the dominant kernel from the committed ncu capture")
+                    help="dram bytes per launch of the dominant kernel from an ncu capture (default: the committed one, "
+                         "N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
