@@ -417,8 +417,8 @@ def run_product_arm(args):
         log(f"R-MAT scale {scale}: build" + (" (relabelled vertices)" if relabelled else ""))
         tag = "_relabelled" if relabelled else ""
         # SpMV shards balance the merge items (rows + nnz); a PageRank shard also updates and sends
-        # every owned row, so rows weigh more there (8 GPUs, multicast exchange: weight 1 / 4 ->
-        # 995 / 1063 iter/s; with unicast peer stores 8 was best, profiles/)
+        # every owned row, so rows weigh more there (8 GPUs, multicast exchange: weight 1 / 4 / 8 ->
+        # 995 / 1063 / 920 iter/s; with unicast peer stores 8 was best, profiles/)
         weight = args.row_weight if args.row_weight >= 0 else (1 if not do_pagerank or world == 1 or relabelled else 4)
         n, bounds, srp, sci, sva, n_edges = build_rmat_shard(torch, gen, scale, 16, seed, rank, world, dev,
                                                             row_weight=weight, relabelled=relabelled)
