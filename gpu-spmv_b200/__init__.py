@@ -389,6 +389,16 @@ def pagerank_device(adj_matrix, d_ranks, config=None):
     return rc, it.value, res.value, conv.value, l1.value
 
 
+def pagerank_device_history(adj_matrix, d_ranks, config=None, capacity=100):
+    """pagerank_device + the L2 residual of every iteration -> (rc, iterations, residual, converged, history)."""
+    it, res, conv = C.c_int(0), C.c_float(0), C.c_bool(False)
+    hist = np.full(capacity, np.nan, dtype=np.float32)
+    cfg = C.byref(config) if config is not None else None
+    rc = lib.spmv_b200_pagerank_device_history(adj_matrix, cfg, dptr(d_ranks), C.byref(it), C.byref(res), C.byref(conv),
+                                               hist.ctypes.data_as(capi.c_float_p), capacity)
+    return rc, it.value, res.value, conv.value, hist
+
+
 # --------------------------------------------------------------- benchmark ----
 
 def make_bench_config(num_warmup_runs=5, num_runs=20, compare_cpu=True):

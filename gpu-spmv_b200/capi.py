@@ -169,6 +169,8 @@ PROTOTYPES = {
     "spmv_b200_ipc_close": (C.c_int, [vp]),
     "spmv_b200_ipc_free": (C.c_int, [vp]),
     "spmv_b200_pr_normalize": (C.c_int, [vp, C.c_int, vp, vp]),
+    "spmv_b200_pagerank_device_history": (C.c_int, [CSR_P, PRC_P, vp, c_int_p, c_float_p, C.POINTER(C.c_bool), c_float_p,
+                                           C.c_int]),
     "spmv_b200_pagerank_device": (C.c_int, [CSR_P, PRC_P, vp, c_int_p, c_float_p, C.POINTER(C.c_bool), c_double_p]),
 }
 

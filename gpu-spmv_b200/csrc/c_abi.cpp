@@ -508,6 +508,16 @@ int spmv_b200_pr_normalize(const float* d_r, int n, float* d_out, void* stream) 
     });
 }
 
+int spmv_b200_pagerank_device_history(const spmv_b200_csr* adj, const spmv_b200_pagerank_config* config, float* d_ranks,
+                                      int* iterations, float* final_residual, bool* converged, float* l2_history,
+                                      int history_capacity) {
+    if (history_capacity < 0 || (history_capacity > 0 && !l2_history)) return kBadArg;
+    return guarded([&] {
+        return b200::pagerank_device(cpp(adj), cpp(config), d_ranks, iterations, final_residual, converged, nullptr, true,
+                                     l2_history, history_capacity);
+    });
+}
+
 int spmv_b200_pagerank_device(const spmv_b200_csr* adj, const spmv_b200_pagerank_config* config, float* d_ranks,
                               int* iterations, float* final_residual, bool* converged, double* l1_residual) {
     return guarded([&] {

@@ -272,7 +272,7 @@ int pr_step(PrPlan* plan, const float* d_r_old, float* d_r_new, float damping, c
 const CsrView& pr_plan_view(const PrPlan* plan);
 double* pr_plan_tmp(PrPlan* plan);
 int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,
-                    float* final_residual, bool* converged, double* l1_residual, bool normalize = true);
+                    float* final_residual, bool* converged, double* l1_residual, bool normalize = true, float* l2_history = nullptr, int history_capacity = 0);
 
 }  // namespace b200
 }  // namespace spmv

@@ -146,7 +146,8 @@ double* pr_plan_tmp(PrPlan* p) { return p->tmp; }
 // The whole loop on one device; d_ranks receives the ranks, normalised on the device with an
 // f64 sum when `normalize` is set, else the raw final iterate.
 int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,
-                    float* final_residual, bool* converged, double* l1_residual, bool normalize) {
+                    float* final_residual, bool* converged, double* l1_residual, bool normalize, float* l2_history,
+                    int history_capacity) {
     if (!adj || !d_ranks) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     PageRankConfig defaults;
     if (!config) config = &defaults;
@@ -220,6 +221,7 @@ int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d
         residual = std::sqrt(static_cast<float>(h_partial[3 * p.slot + 0]));  // L2 norm of the delta (:118)
         l1 = h_partial[3 * p.slot + 1];
         iters = p.iter;
+        if (l2_history && p.iter >= 1 && p.iter <= history_capacity) l2_history[p.iter - 1] = residual;
         fin = p.vec;
         return residual < config->tolerance;  // :123-127
     };

@@ -437,6 +437,16 @@ SPMV_B200_API int spmv_b200_pagerank_device(const spmv_b200_csr* adj,
                                             float* final_residual, bool* converged,
                                             double* l1_residual);
 
+/* the same loop, also reporting the residual of every iteration: l2_history[i]
+ * (host array of history_capacity floats) receives the L2 norm of the delta after iteration i + 1,
+ * i.e. the quantity the stop rule compares with the tolerance (src/pagerank.cu:118-127);
+ * entries beyond *iterations are left untouched. */
+SPMV_B200_API int spmv_b200_pagerank_device_history(const spmv_b200_csr* adj,
+                                                    const spmv_b200_pagerank_config* config,
+                                                    float* d_ranks, int* iterations,
+                                                    float* final_residual, bool* converged,
+                                                    float* l2_history, int history_capacity);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -227,3 +227,25 @@ def test_device_top_k_matches_host_top_k(sp, cuda, n, k, kind):
     assert np.array_equal(v[ids], vals) and len(set(ids.tolist())) == kk
     expect = np.lexsort((np.arange(n), -v.astype(np.float64)))[:kk]  # rank descending, id ascending
     assert np.array_equal(ids, expect.astype(np.int32))
+
+
+def test_residual_history(sp, orc, cuda):
+    """spmv_b200_pagerank_device_history: the residual of every iteration is the one the stop rule saw
+    (last entry == final_residual < tolerance, earlier ones above it, nothing written past the last iteration)
+    and matches the f64 restatement of the recurrence run for the same number of iterations."""
+    gen = gen_mod()
+    n, rp, ci, va = gen.rmat_pagerank_csr(13, 8, 21, cuda)
+    G = sp.DeviceCSR(n, n, rp, ci, va)
+    d_ranks = torch.empty(n, device=cuda)
+    rc, iters, res, conv, hist = sp.pagerank_device_history(G.ptr, d_ranks, sp.make_pagerank_config(0.85, 1e-6, 100), 64)
+    assert rc == 0 and conv and 1 < iters <= 64
+    assert np.all(np.isfinite(hist[:iters])) and np.all(np.isnan(hist[iters:]))
+    assert hist[iters - 1] == np.float32(res) and res < 1e-6 and np.all(hist[:iters - 1] >= 1e-6)
+    assert hist[iters - 1] < hist[0]
+    for k in (1, iters // 2, iters):
+        _, _, l2, _, _ = orc.pagerank_f64(n, n, rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy(), 0.85, 1e-6, 100,
+                                          fixed_it=k)
+        assert abs(hist[k - 1] - l2) <= 1e-8 + 1e-3 * l2
+    # a capacity shorter than the run keeps the first entries only
+    rc, iters2, _, _, short = sp.pagerank_device_history(G.ptr, d_ranks, sp.make_pagerank_config(0.85, 1e-6, 100), 3)
+    assert rc == 0 and iters2 == iters and np.array_equal(short, hist[:3])
