@@ -328,7 +328,8 @@ SPMV_B200_API int spmv_b200_csr_normalize_columns_device(spmv_b200_csr* A);
  * carries the row starts.  The caller's arrays are not modified;
  * d_values is read live at every product, d_row_ptrs / d_col_indices must not change while the
  * plan is alive.  max_hot_columns <= 0: the tuned default (24576 on B200; the table competes with
- * the L1 for the same 256 KB).
+ * the L1 for the same 256 KB).  A plan owns the work arrays of a product, so it serves ONE product at
+ * a time: use one plan per stream (or order the products).
  * force != 0 skips the size / benefit thresholds (tests).
  */
 typedef struct spmv_b200_csr_plan spmv_b200_csr_plan;
