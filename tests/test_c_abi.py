@@ -123,3 +123,37 @@ def test_device_entry_points_fail_loudly_without_gpu(sp):
     A.contents.d_col_indices = None
     A.contents.d_values = None
     sp.csr_destroy(A)
+
+
+def test_extension_entry_points_validate_their_arguments(sp):
+    """The additive entry points (plans, assembly, top-k, multicast step) reject bad arguments with the
+    reference's codes before touching the device (so this runs without a GPU)."""
+    import ctypes as C
+    L = sp.lib
+    bad_arg, bad_fmt = int(sp.SpMVError.INVALID_ARGUMENT), int(sp.SpMVError.INVALID_FORMAT)
+    handle = C.c_void_p()
+    assert L.spmv_b200_csr_plan_create(None, 0, 0, C.byref(handle)) == bad_arg
+    A = sp.csr_create(0, 0, 0)
+    sp.csr_from_dense(A, np.eye(4, dtype=np.float32), 4, 4)
+    assert L.spmv_b200_csr_plan_create(A, 0, 0, None) == bad_arg
+    assert L.spmv_b200_csr_plan_create(A, 0, 0, C.byref(handle)) == bad_fmt  # host arrays only: not on the device
+    assert not handle.value
+    assert L.spmv_b200_spmv_csr_planned(None, None, None, None) == bad_arg
+    assert L.spmv_b200_csr_plan_info(None, None, None, None) == bad_arg
+    L.spmv_b200_csr_plan_destroy(None)
+    L.spmv_b200_csr_forget_plan(None)
+    assert sp.csr_auto_plan_info(A) == (0, 0)
+    assert L.spmv_b200_csr_from_coo_device(None, 1, 1, 0, None, None, None) == bad_arg
+    assert L.spmv_b200_csr_from_coo_device(A, -1, 1, 0, None, None, None) == bad_arg
+    assert L.spmv_b200_csr_from_coo_device(A, 1, 1, 5, None, None, None) == bad_arg
+    assert (A.contents.num_rows, A.contents.nnz) == (4, 4)  # untouched
+    assert L.spmv_b200_csr_normalize_columns_device(None) == bad_arg
+    assert L.spmv_b200_csr_normalize_columns_device(A) == bad_fmt
+    node = (sp.TopKNode * 1)()
+    assert L.spmv_b200_pagerank_top_k_device(None, 4, 1, node) == bad_arg
+    assert L.spmv_b200_pagerank_top_k_device(16, -1, 1, node) == bad_arg
+    assert L.spmv_b200_pagerank_top_k_device(16, 4, 0, node) == 0  # nothing to do
+    assert L.spmv_b200_pr_step_multicast(None, None, None, 0.85, None, None, None, None, 2, 0, None) == bad_arg
+    assert L.spmv_b200_pr_plan_set_hot(None, 0, 0, None) == bad_arg
+    assert L.spmv_b200_pagerank_device_history(A, None, None, None, None, None, None, -1) == bad_arg
+    sp.csr_destroy(A)
