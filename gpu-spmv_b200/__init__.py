@@ -478,21 +478,27 @@ def csr_normalize_columns_device(A):
 class CsrPlan:
     """Merge coordinates + hub-column table of a device CSR (spmv_b200_csr_plan)."""
 
-    def __init__(self, A, max_hot_columns=0, force=False):
+    def __init__(self, A, max_hot_columns=0, force=False, snapshot_values=False):
         self.handle = C.c_void_p()
-        rc = lib.spmv_b200_csr_plan_create(A, int(max_hot_columns), int(bool(force)), C.byref(self.handle))
+        flags = (1 if force else 0) | (2 if snapshot_values else 0)
+        rc = lib.spmv_b200_csr_plan_create(A, int(max_hot_columns), flags, C.byref(self.handle))
         if rc != 0:
             raise RuntimeError(f"csr_plan_create: {spmv_error_string(rc)}")
         self._A = A  # the plan reads the matrix's device arrays
 
     def info(self):
-        """(hot_columns, hot_nnz, mode); mode 0 plain tile kernel, 1 hub table, 2 all of x."""
+        """(hot_columns, hot_nnz, mode); mode 0 plain tile kernel, 1 / 2 hub-column kernel (table / all of x),
+        3 / 4 segmented stream, 5 ELL layout (snapshot of the values)."""
         n, z, m = C.c_int(0), C.c_longlong(0), C.c_int(0)
         lib.spmv_b200_csr_plan_info(self.handle, C.byref(n), C.byref(z), C.byref(m))
         return n.value, z.value, m.value
 
     def spmv(self, d_x, d_y, stream=0):
         return lib.spmv_b200_spmv_csr_planned(self.handle, dptr(d_x), dptr(d_y), C.c_void_p(stream))
+
+    def refresh_values(self, stream=0):
+        """Re-reads d_values into the ELL snapshot of a mode-5 plan (no-op otherwise)."""
+        return lib.spmv_b200_csr_plan_refresh_values(self.handle, C.c_void_p(stream))
 
     def close(self):
         if self.handle:

@@ -151,6 +151,7 @@ PROTOTYPES = {
     "spmv_b200_csr_normalize_columns_device": (C.c_int, [CSR_P]),
     "spmv_b200_csr_plan_create": (C.c_int, [CSR_P, C.c_int, C.c_int, C.POINTER(vp)]),
     "spmv_b200_csr_plan_destroy": (None, [vp]),
+    "spmv_b200_csr_plan_refresh_values": (C.c_int, [vp, vp]),
     "spmv_b200_csr_plan_info": (C.c_int, [vp, c_int_p, C.POINTER(C.c_longlong), c_int_p]),
     "spmv_b200_spmv_csr_planned": (C.c_int, [vp, vp, vp, vp]),
     "spmv_b200_csr_forget_plan": (None, [CSR_P]),

@@ -377,10 +377,15 @@ int spmv_b200_csr_normalize_columns_device(spmv_b200_csr* A) {
 
 int spmv_b200_csr_plan_create(const spmv_b200_csr* A, int max_hot_columns, int force, spmv_b200_csr_plan** out) {
     return guarded([&] {
-        return b200::csr_plan_create(cpp(A), max_hot_columns, force != 0, reinterpret_cast<b200::CsrPlan**>(out));
+        return b200::csr_plan_create(cpp(A), max_hot_columns, force, reinterpret_cast<b200::CsrPlan**>(out));
     });
 }
 void spmv_b200_csr_plan_destroy(spmv_b200_csr_plan* plan) { b200::csr_plan_destroy(reinterpret_cast<b200::CsrPlan*>(plan)); }
+int spmv_b200_csr_plan_refresh_values(spmv_b200_csr_plan* plan, void* stream) {
+    return guarded([&] {
+        return b200::csr_plan_refresh_values(reinterpret_cast<b200::CsrPlan*>(plan), static_cast<cudaStream_t>(stream));
+    });
+}
 int spmv_b200_csr_plan_info(const spmv_b200_csr_plan* plan, int* hot_columns, long long* hot_nnz, int* mode) {
     if (!plan) return kBadArg;
     b200::csr_plan_info(reinterpret_cast<const b200::CsrPlan*>(plan), hot_columns, hot_nnz, mode);

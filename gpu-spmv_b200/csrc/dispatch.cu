@@ -86,7 +86,34 @@ struct CsrPlan {
     PlannedCsr planned;
     Scratch merge_block;
     MergePlan merge;
+    // Opt-in (kPlanSnapshotValues): a uniform matrix is re-laid out as ELL on the device and
+    // multiplied by the ELL kernel; ell_values is a SNAPSHOT of A.values (csr_plan_refresh_values).
+    int ell_width = 0;
+    float* ell_values = nullptr;
+    int* ell_cols = nullptr;
 };
+
+constexpr int kPlanForce = 1;           // flags of csr_plan_create
+constexpr int kPlanSnapshotValues = 2;
+constexpr int kEllPlanMaxWidth = 8;     // the TMA-staged ELL pipeline (ell_kernels.cu) covers W <= 8
+
+// ELL routing pays when the padding is small: rows * width <= 1.125 * nnz
+static bool ell_route_worthwhile(const CsrView& A, int width) {
+    return width >= 1 && width <= kEllPlanMaxWidth &&
+           static_cast<long long>(A.rows) * width * 8 <= static_cast<long long>(A.nnz) * 9;
+}
+
+static cudaError_t longest_row(const CsrView& A, int* out, cudaStream_t stream) {
+    int* d_w = nullptr;
+    cudaError_t e = cudaMalloc(&d_w, sizeof(int));
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(d_w, 0, sizeof(int), stream);
+    e = launch_max_row_len(A, d_w, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_w, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d_w);
+    return e;
+}
 
 // SPMV_B200_PLAN=hub|seg forces one of the planned kernels (tuning / tests); default: by structure
 static int plan_kind_env() {
@@ -116,7 +143,8 @@ cudaError_t planned_build(const CsrView& A, PlannedCsr* out, int capacity, bool 
     return seg_plan_build(A, &out->seg, capacity, force, stream);
 }
 
-int csr_plan_create(const CSRMatrix* A, int max_hot_columns, bool force, CsrPlan** out) {
+int csr_plan_create(const CSRMatrix* A, int max_hot_columns, int flags, CsrPlan** out) {
+    const bool force = (flags & kPlanForce) != 0;
     if (!A || !out) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     if (!A->d_row_ptrs || !A->d_col_indices || (A->nnz > 0 && !A->d_values))
         return static_cast<int>(SpMVError::INVALID_FORMAT);
@@ -131,12 +159,32 @@ int csr_plan_create(const CSRMatrix* A, int max_hot_columns, bool force, CsrPlan
             return static_cast<int>(SpMVError::CUDA_MALLOC);
         }
         p->merge = merge_plan_carve(block, p->A.rows, p->A.nnz, false);
-        cudaError_t e = launch_merge_partition(p->A, p->merge, stream);
-        if (e == cudaSuccess) e = planned_build(p->A, &p->planned, max_hot_columns, force, true, stream);
+        cudaError_t e = cudaSuccess;
+        if (flags & kPlanSnapshotValues) {  // uniform matrix -> ELL layout, if the caller accepts a value snapshot
+            int width = 0;
+            e = longest_row(p->A, &width, stream);
+            if (e == cudaSuccess && ell_route_worthwhile(p->A, width)) {
+                const size_t slots = static_cast<size_t>(p->A.rows) * width;
+                if (cudaMalloc(&p->ell_values, slots * sizeof(float)) == cudaSuccess &&
+                    cudaMalloc(&p->ell_cols, slots * sizeof(int)) == cudaSuccess) {
+                    p->ell_width = width;
+                    e = launch_ell_from_csr(p->A, width, p->ell_values, p->ell_cols, stream);
+                } else {
+                    cudaGetLastError();
+                    cudaFree(p->ell_values);
+                    p->ell_values = nullptr;
+                }
+            }
+        }
+        if (e == cudaSuccess) e = launch_merge_partition(p->A, p->merge, stream);
+        if (e == cudaSuccess && p->ell_width == 0)
+            e = planned_build(p->A, &p->planned, max_hot_columns, force, true, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) {
             cudaGetLastError();
             p->planned.release();
+            cudaFree(p->ell_values);
+            cudaFree(p->ell_cols);
             delete p;
             return static_cast<int>(e == cudaErrorMemoryAllocation ? SpMVError::CUDA_MALLOC : SpMVError::KERNEL_LAUNCH);
         }
@@ -148,6 +196,8 @@ int csr_plan_create(const CSRMatrix* A, int max_hot_columns, bool force, CsrPlan
 void csr_plan_destroy(CsrPlan* p) {
     if (!p) return;
     p->planned.release();
+    cudaFree(p->ell_values);
+    cudaFree(p->ell_cols);
     delete p;
 }
 
@@ -156,7 +206,8 @@ void csr_plan_info(const CsrPlan* p, int* hot_columns, long long* hot_nnz, int* 
     if (hot_columns) *hot_columns = !p ? 0 : (seg ? p->planned.seg.n_hot : p->planned.hot.n_hot);
     if (hot_nnz) *hot_nnz = !p ? 0 : (seg ? p->planned.seg.hot_nnz : p->planned.hot.hot_nnz);
     if (mode) {
-        if (seg) *mode = p->planned.seg.whole_x ? 4 : 3;
+        if (p && p->ell_width > 0) *mode = 5;
+        else if (seg) *mode = p->planned.seg.whole_x ? 4 : 3;
         else *mode = !p || p->planned.hot.n_hot <= 0 ? 0 : (p->planned.hot.all_hot ? 2 : 1);
     }
 }
@@ -167,10 +218,22 @@ int spmv_csr_planned(const CsrPlan* p, const float* d_x, float* d_y, cudaStream_
     if (A.rows <= 0) return 0;
     cudaError_t e;
     if (A.nnz <= 0) e = launch_csr_stream(A, d_x, d_y, 1, stream);  // writes zeros
+    else if (p->ell_width > 0) e = launch_ell(A.rows, p->ell_width, p->ell_cols, p->ell_values, d_x, d_y, nullptr, stream);
     else if (p->planned.seg.valid()) e = launch_seg_spmv(A, p->planned.seg, d_x, d_y, stream);
     else if (p->planned.hot.n_hot > 0) e = launch_hot_spmv(A, p->planned.hot, d_x, d_y, p->merge, stream);
     else e = launch_merge_spmv(A, d_x, d_y, p->merge, stream);
     if (e != cudaSuccess) {
+        cudaGetLastError();
+        return static_cast<int>(SpMVError::KERNEL_LAUNCH);
+    }
+    return 0;
+}
+
+// re-reads A.values into the ELL snapshot of a mode-5 plan (no-op for the other modes); stream-ordered
+int csr_plan_refresh_values(CsrPlan* p, cudaStream_t stream) {
+    if (!p) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
+    if (p->ell_width <= 0) return 0;
+    if (launch_ell_from_csr(p->A, p->ell_width, p->ell_values, p->ell_cols, stream) != cudaSuccess) {
         cudaGetLastError();
         return static_cast<int>(SpMVError::KERNEL_LAUNCH);
     }

@@ -247,7 +247,10 @@ cudaError_t dispatch_csr(const CsrView& A, const float* x, float* y, int kernel_
 
 // ---- explicit CSR plans (dispatch.cu): merge coordinates + hub-column plan, built once ------
 struct CsrPlan;
-int csr_plan_create(const CSRMatrix* A, int max_hot_columns, bool force, CsrPlan** out);
+// flags: 1 = force (skip the size / benefit thresholds), 2 = the caller accepts a SNAPSHOT of the values
+// (uniform matrices are then re-laid out as ELL; csr_plan_refresh_values re-reads them)
+int csr_plan_create(const CSRMatrix* A, int max_hot_columns, int flags, CsrPlan** out);
+int csr_plan_refresh_values(CsrPlan* plan, cudaStream_t stream);
 void csr_plan_destroy(CsrPlan* plan);
 void csr_plan_info(const CsrPlan* plan, int* hot_columns, long long* hot_nnz, int* mode);
 int spmv_csr_planned(const CsrPlan* plan, const float* d_x, float* d_y, cudaStream_t stream);

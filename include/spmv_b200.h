@@ -328,18 +328,28 @@ SPMV_B200_API int spmv_b200_csr_normalize_columns_device(spmv_b200_csr* A);
  * carries the row starts.  The caller's arrays are not modified;
  * d_values is read live at every product, d_row_ptrs / d_col_indices must not change while the
  * plan is alive.  max_hot_columns <= 0: the tuned default (24576 on B200; the table competes with
- * the L1 for the same 256 KB).  A plan owns the work arrays of a product, so it serves ONE product at
+ * the L1 for the same 256 KB).  flags: SPMV_B200_PLAN_* below.  A plan owns the work arrays of a product, so it serves ONE product at
  * a time: use one plan per stream (or order the products).
- * force != 0 skips the size / benefit thresholds (tests).
  */
 typedef struct spmv_b200_csr_plan spmv_b200_csr_plan;
-SPMV_B200_API int spmv_b200_csr_plan_create(const spmv_b200_csr* A, int max_hot_columns, int force,
+#define SPMV_B200_PLAN_FORCE 1            /* skip the size / benefit thresholds (tests) */
+#define SPMV_B200_PLAN_SNAPSHOT_VALUES 2  /* see below */
+SPMV_B200_API int spmv_b200_csr_plan_create(const spmv_b200_csr* A, int max_hot_columns, int flags,
                                             spmv_b200_csr_plan** out);
+/* With SPMV_B200_PLAN_SNAPSHOT_VALUES the caller allows the plan to keep its own copy of the VALUES:
+ * a uniform matrix (longest row <= 8 and rows * longest <= 1.125 * nnz) is then re-laid out as
+ * column-major ELL on the device (ell_from_csr semantics, src/ell_matrix.cpp:111-159) and multiplied
+ * by the ELL kernel -- the routing the reference's ELL_KERNEL enumerator promises but
+ * spmv_auto_config never performs (spmv.h:16, src/spmv_cpu.cpp:41-47); mode 5, bit-identical to
+ * SCALAR_CSR / spmv_cpu_csr.  After changing d_values call this to re-read them (stream-ordered;
+ * a no-op for the other modes, which read d_values live). */
+SPMV_B200_API int spmv_b200_csr_plan_refresh_values(spmv_b200_csr_plan* plan, void* stream);
 SPMV_B200_API void spmv_b200_csr_plan_destroy(spmv_b200_csr_plan* plan);
 /* hot_columns: table entries in use; hot_nnz: non-zeros served by the table;
  * mode: 0 plain merge-path tile kernel with precomputed coordinates,
  *       1 hub-column merge-path kernel, 2 the same with the whole x in the table,
- *       3 segmented-stream kernel (csr_seg_kernels.cu), 4 the same with the whole x in the table */
+ *       3 segmented-stream kernel (csr_seg_kernels.cu), 4 the same with the whole x in the table,
+ *       5 ELL layout + ELL kernel (only with SPMV_B200_PLAN_SNAPSHOT_VALUES) */
 SPMV_B200_API int spmv_b200_csr_plan_info(const spmv_b200_csr_plan* plan, int* hot_columns,
                                           long long* hot_nnz, int* mode);
 /* y = A x through the plan; stream-ordered (stream is a cudaStream_t), no sync, no timing.

@@ -304,3 +304,43 @@ def test_full_size_rmat24_properties(sp, cuda):
     torch.cuda.synchronize()
     assert torch.equal(y2, y_p * 2)
     plan.close()
+
+
+def test_snapshot_plan_routes_uniform_matrices_to_ell(sp, orc, cuda):
+    """SPMV_B200_PLAN_SNAPSHOT_VALUES: a uniform matrix is re-laid out as ELL inside the plan (the
+    routing the reference's ELL_KERNEL enumerator promises, spmv.h:16).  The ELL kernel keeps the CSR
+    order inside a row, so the result is BIT-IDENTICAL to spmv_cpu_csr; new values need
+    refresh_values(); a skewed matrix ignores the flag."""
+    gen = gen_mod()
+    grid = 700
+    n = grid * grid
+    rp, ci, va = gen.laplacian_2d_csr(grid, cuda)
+    A = sp.DeviceCSR(n, n, rp, ci, va)
+    x = gen.vector_pm1(n, 8, cuda)
+    plan = sp.CsrPlan(A.ptr, snapshot_values=True)
+    assert plan.info()[2] == 5
+    y = torch.full((n,), float("nan"), device=cuda)
+    assert plan.spmv(x, y) == 0
+    torch.cuda.synchronize()
+    expect = orc.spmv_csr(n, rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy(), x.cpu().numpy())
+    assert np.array_equal(bits(y.cpu().numpy()), bits(expect))
+    va.mul_(1.5).add_(0.25)  # same pattern, new values
+    assert plan.spmv(x, y) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(y.cpu().numpy()), bits(expect))  # the snapshot is still the old one
+    assert plan.refresh_values() == 0
+    assert plan.spmv(x, y) == 0
+    torch.cuda.synchronize()
+    expect2 = orc.spmv_csr(n, rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy(), x.cpu().numpy())
+    assert np.array_equal(bits(y.cpu().numpy()), bits(expect2)) and not np.array_equal(bits(expect), bits(expect2))
+    plan.close()
+    # without the flag the same matrix takes a kernel that reads the values live
+    live = sp.CsrPlan(A.ptr, force=True)
+    assert live.info()[2] in (0, 3)
+    live.close()
+    # a skewed matrix is not ELL material: the flag changes nothing
+    n2, rp2, ci2, va2 = gen.rmat_pagerank_csr(14, 16, 3, cuda)
+    A2 = sp.DeviceCSR(n2, n2, rp2, ci2, va2)
+    p2 = sp.CsrPlan(A2.ptr, 64, force=True, snapshot_values=True)
+    assert p2.info()[2] in (1, 3)
+    p2.close()
