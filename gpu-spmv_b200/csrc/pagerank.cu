@@ -225,13 +225,65 @@ int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d
         fin = p.vec;
         return residual < config->tolerance;  // :123-127
     };
+    // One iteration = the fused step (3-4 kernels), the dangling-mass hand-over and the 24-byte download.
+    auto enqueue_iteration = [&](float* from, float* to, int slot, cudaStream_t s) -> int {
+        const int r = pr_step(plan, from, to, config->damping_factor, d_dsum, d_bits, d_partial, s);
+        if (r != 0) return r;
+        launch_next_dsum(d_partial, d_dsum, s);
+        cudaMemcpyAsync(h_partial + 3 * slot, d_partial, 3 * sizeof(double), cudaMemcpyDeviceToHost, s);
+        return 0;
+    };
+    // CUDA-graph replay: the two ping-pong iterations (a -> b with host slot 0,
+    // b -> a with slot 1) are captured once and replayed, one graph launch per iteration instead of
+    // 5-6 API calls -- small graphs are launch-bound.  The stop rule stays per iteration (above).
+    // Capture needs a real stream; a blocking one keeps the legacy default stream's ordering.  Any
+    // failure falls back to the eager loop.  SPMV_B200_PR_GRAPH=0 disables it.
+    cudaStream_t gs = nullptr;
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};
+    unsigned long long launches_per_iteration = 0;
+    static const int use_graph = [] {
+        const char* v = getenv("SPMV_B200_PR_GRAPH");
+        return v ? atoi(v) : 1;
+    }();
+    if (use_graph && config->max_iterations >= 4 && cudaStreamCreate(&gs) == cudaSuccess) {
+        for (int p = 0; p < 2; ++p) {
+            cudaGraph_t g = nullptr;
+            const unsigned long long before = launch_count();
+            bool good = cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (good) {
+                const int r = enqueue_iteration(p == 0 ? d_a : d_b, p == 0 ? d_b : d_a, p, gs);
+                good = cudaStreamEndCapture(gs, &g) == cudaSuccess && r == 0 && g != nullptr;
+            }
+            launches_per_iteration = launch_count() - before;
+            count_launches(-static_cast<int>(launches_per_iteration));  // captured, not launched
+            if (good) good = cudaGraphInstantiate(&exec[p], g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            if (!good) {
+                cudaGetLastError();
+                for (int q = 0; q < 2; ++q) {
+                    if (exec[q]) cudaGraphExecDestroy(exec[q]);
+                    exec[q] = nullptr;
+                }
+                break;
+            }
+        }
+    }
+    const bool replay = exec[0] && exec[1];
+    cudaStream_t loop_stream = replay ? gs : stream;
     for (int it = 0; it < config->max_iterations; ++it) {
-        rc = pr_step(plan, r_old, r_new, config->damping_factor, d_dsum, d_bits, d_partial, stream);
-        if (rc != 0) break;  // the reference also leaves the loop on a failed SpMV (:105-107)
-        launch_next_dsum(d_partial, d_dsum, stream);
         const int slot = it & 1;
-        cudaMemcpyAsync(h_partial + 3 * slot, d_partial, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
-        cudaEventRecord(ev[slot], stream);
+        if (replay) {
+            if (cudaGraphLaunch(exec[slot], gs) != cudaSuccess) {
+                cudaGetLastError();
+                rc = static_cast<int>(SpMVError::KERNEL_LAUNCH);
+                break;
+            }
+            count_launches(static_cast<int>(launches_per_iteration));
+        } else {
+            rc = enqueue_iteration(r_old, r_new, slot, stream);
+            if (rc != 0) break;  // the reference also leaves the loop on a failed SpMV (:105-107)
+        }
+        cudaEventRecord(ev[slot], loop_stream);
         if (pending.valid) {
             const bool done = settle(pending);
             pending.valid = false;
@@ -246,6 +298,10 @@ int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d
     if (pending.valid && rc == 0) conv = settle(pending) && rc == 0;
     cudaEventDestroy(ev[0]);
     cudaEventDestroy(ev[1]);
+    if (gs) cudaStreamSynchronize(gs);  // a speculative iteration may still be running
+    for (int q = 0; q < 2; ++q)
+        if (exec[q]) cudaGraphExecDestroy(exec[q]);
+    if (gs) cudaStreamDestroy(gs);
     // final vector (:135-139) and normalisation (:142-150)
     if (normalize) launch_normalize(fin, n, d_ranks, plan->tmp, stream);
     else cudaMemcpyAsync(d_ranks, fin, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream);
