@@ -1,0 +1,51 @@
+"""bench.py's output contract: the reference arm (runs here, CPU only) and the committed product-arm
+lines (measured on B200, profiles/) carry every key the driver and the judge read."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"}
+
+
+def test_reference_arm_prints_one_contract_line():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["impl"] == "reference" and d["metric"] == "spmv_effective_hbm_gbs" and d["unit"] == "GB/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32" and d["n_gpus"] == 1
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["sample"] and cb["value"] == d["value"] > 0
+    e2e = d["e2e"]
+    assert e2e["value"] == d["value"] and e2e["unit"] == d["unit"]
+    assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+    assert d["gpu_launches"] == 0
+
+
+def test_committed_product_lines_have_every_contract_key():
+    for name, n in (("bench_r1_final_n1.json", 1), ("bench_r1_final_n8.json", 8)):
+        text = open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1]
+        d = json.loads(text)
+        assert (BASE_KEYS | {"clocks", "roofline"}) <= set(d), name
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["data"] == "synthetic" and d["gpu_launches"] == d["steps"] > 0
+        assert d["warmup"] >= 3 and d["value"] > 0 and d["ms_per_step"] > 0
+        assert "workload" in d["config"] and "l2" in d["config"]
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm"
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        c = d["clocks"]
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(c)
+        assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+        e = d["e2e"]
+        assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+        if n == 1:
+            cb = d["cpu_baseline"]
+            assert cb["kind"] == "reference" and cb["cores"] == 1 and cb["value"] > 0 and cb["sample"]
+            assert r["traffic"] is not None
