@@ -61,6 +61,10 @@ int pr_plan_create(const CSRMatrix* shard, int row_offset, int n_global, cudaStr
     if (!shard || !out || row_offset < 0 || n_global < 0) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     if (static_cast<long long>(row_offset) + shard->num_rows > n_global)
         return static_cast<int>(SpMVError::INVALID_DIMENSION);
+    // every kernel gathers r[col] for col < num_cols from a rank vector of n_global entries: a shard (or a whole
+    // adjacency matrix) with another column count would read past it.  The reference rejects the same input in
+    // spmv_csr(..., vec_size = n) -> INVALID_DIMENSION (src/spmv_kernels.cu:224-226, src/pagerank.cu:102-107).
+    if (shard->num_cols != n_global) return static_cast<int>(SpMVError::INVALID_DIMENSION);
     if (!shard->d_row_ptrs || (shard->nnz > 0 && (!shard->d_col_indices || !shard->d_values)))
         return static_cast<int>(SpMVError::INVALID_FORMAT);
     PrPlan* p = new (std::nothrow) PrPlan();
@@ -157,6 +161,9 @@ int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d
     if (converged) *converged = false;
     if (l1_residual) *l1_residual = 0.0;
     if (n <= 0) return 0;
+    // non-square adjacency: the reference's first spmv_csr(adj, ..., vec_size = n) fails with INVALID_DIMENSION and
+    // pagerank() returns the uniform vector with iterations = 0 (src/pagerank.cu:102-107); pagerank() below does the same
+    if (adj->num_cols != n) return static_cast<int>(SpMVError::INVALID_DIMENSION);
 
     cudaStream_t stream = nullptr;
     PrPlan* plan = nullptr;

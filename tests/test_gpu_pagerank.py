@@ -249,3 +249,33 @@ def test_residual_history(sp, orc, cuda):
     # a capacity shorter than the run keeps the first entries only
     rc, iters2, _, _, short = sp.pagerank_device_history(G.ptr, d_ranks, sp.make_pagerank_config(0.85, 1e-6, 100), 3)
     assert rc == 0 and iters2 == iters and np.array_equal(short, hist[:3])
+
+
+def test_non_square_adjacency_is_rejected(sp, ref, cuda):
+    """A matrix with num_cols != num_rows: the reference's first spmv_csr(adj, ..., vec_size = n) returns
+    INVALID_DIMENSION, the loop breaks and pagerank() hands back the uniform vector with iterations = 0
+    (src/pagerank.cu:102-107, :135-150).  The device entry points must reject it instead of gathering
+    past the rank vector."""
+    gen = gen_mod()
+    rows, cols = 64, 96
+    rp, ci, va = gen.random_csr(rows, cols, 4, seed=8, device="cpu")
+    rp, ci, va = rp.numpy(), ci.numpy(), va.numpy()
+    G = sp.csr_from_arrays(rows, cols, rp, ci, va)
+    assert sp.csr_to_gpu(G) == 0
+    res, ranks = sp.pagerank(G, sp.make_pagerank_config(0.85, 1e-6, 50))
+    assert res.iterations == 0 and not res.converged
+    assert np.allclose(ranks, 1.0 / rows, rtol=1e-6)
+    sp.pagerank_free(res)
+    d_ranks = torch.empty(rows, device=cuda)
+    rc = sp.pagerank_device(G, d_ranks, sp.make_pagerank_config(0.85, 1e-6, 50))[0]
+    assert rc == sp.SpMVError.INVALID_DIMENSION
+    handle = C.c_void_p()
+    assert sp.lib.spmv_b200_pr_plan_create(G, 0, rows, None, C.byref(handle)) == sp.SpMVError.INVALID_DIMENSION
+    # the reference library itself (oracle/_ref: GPU SpMV + host loops) behaves the same way
+    h, keep = ref.csr_wrap(rows, cols, rp, ci, va)
+    assert ref.L.ref_csr_to_gpu(h) == 0
+    r_ref = np.empty(rows, np.float32)
+    r_res, r_conv = C.c_float(0), C.c_int(0)
+    it_ref = ref.L.ref_pagerank(h, 0.85, 1e-6, 50, r_ref.ctypes.data_as(C.POINTER(C.c_float)), C.byref(r_res), C.byref(r_conv))
+    assert it_ref == 0 and not r_conv.value and np.array_equal(r_ref, ranks)
+    sp.csr_destroy(G)
