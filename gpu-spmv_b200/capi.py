@@ -140,6 +140,23 @@ PROTOTYPES = {
     "spmv_b200_reference_policy": (C.c_int, [CSR_P, CFG_P]),
     "spmv_b200_spmv_csr_async": (C.c_int, [CSR_P, vp, vp, CFG_P, vp]),
     "spmv_b200_spmv_ell_async": (C.c_int, [ELL_P, vp, vp, vp]),
+    "spmv_b200_pagerank_multi": (C.c_int, [CSR_P, vp, C.c_int, c_int_p, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "spmv_b200_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(vp)]),
+    "spmv_b200_comm_destroy": (None, [vp]),
+    "spmv_b200_comm_barrier": (C.c_int, [vp]),
+    "spmv_b200_comm_allgather": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "spmv_b200_comm_allgather_fds": (C.c_int, [vp, C.c_int, c_int_p]),
+    "spmv_b200_pr_dist_create": (C.c_int, [vp, CSR_P, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "spmv_b200_pr_dist_run": (C.c_int, [vp, vp, C.c_int, vp]),
+    "spmv_b200_pr_dist_ranks": (vp, [vp]),
+    "spmv_b200_pr_dist_exchange": (C.c_int, [vp]),
+    "spmv_b200_pr_dist_hub_columns": (C.c_int, [vp]),
+    "spmv_b200_pr_dist_destroy": (None, [vp]),
+    "spmv_b200_nccl_available": (C.c_int, []),
+    "spmv_b200_ell_host_plan_create": (C.c_int, [ELL_P, C.c_int, C.POINTER(vp)]),
+    "spmv_b200_ell_host_plan_destroy": (None, [vp]),
+    "spmv_b200_spmv_ell_host": (C.c_int, [vp, vp, vp]),
+    "spmv_b200_ell_host_plan_info": (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
     "spmv_b200_ell_from_csr_device": (C.c_int, [ELL_P, CSR_P]),
     "spmv_b200_merge_path_search": (C.c_int, [C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p]),
     "spmv_b200_partition_rows": (C.c_int, [c_int_p, C.c_int, C.c_int, c_int_p]),
@@ -155,6 +172,8 @@ PROTOTYPES = {
     "spmv_b200_csr_plan_info": (C.c_int, [vp, c_int_p, C.POINTER(C.c_longlong), c_int_p]),
     "spmv_b200_spmv_csr_planned": (C.c_int, [vp, vp, vp, vp]),
     "spmv_b200_csr_forget_plan": (None, [CSR_P]),
+    "spmv_b200_set_auto_plan": (None, [C.c_int]),
+    "spmv_b200_auto_plan_enabled": (C.c_int, []),
     "spmv_b200_csr_auto_plan_info": (C.c_int, [CSR_P, c_int_p, C.POINTER(C.c_longlong)]),
     "spmv_b200_pr_plan_set_hot": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "spmv_b200_pr_plan_create": (C.c_int, [CSR_P, C.c_int, C.c_int, vp, C.POINTER(vp)]),

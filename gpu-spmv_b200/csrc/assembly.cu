@@ -56,12 +56,12 @@ __global__ void coo_row_ptrs_kernel(long long n, int rows, const unsigned long l
 }
 
 __global__ void divide_by_colsum_kernel(int nnz, int cols, const int* __restrict__ col_indices,
-                                        const float* __restrict__ colsum, float* __restrict__ values) {
+                                        const double* __restrict__ colsum, float* __restrict__ values) {
     for (long long j = blockIdx.x * static_cast<long long>(kBlock) + threadIdx.x; j < nnz;
          j += static_cast<long long>(gridDim.x) * kBlock) {
         const int c = col_indices[j];
         if (c < 0 || c >= cols) continue;
-        const float s = __ldg(colsum + c);
+        const float s = static_cast<float>(__ldg(colsum + c));
         if (s != 0.0f) values[j] = __fdiv_rn(values[j], s);
     }
 }
@@ -157,12 +157,12 @@ int csr_normalize_columns_device(CSRMatrix* A) {
     if (A->nnz <= 0 || A->num_cols <= 0) return 0;
     if (!A->d_col_indices || !A->d_values || !A->d_row_ptrs) return static_cast<int>(SpMVError::INVALID_FORMAT);
     cudaStream_t stream = nullptr;
-    float* d_colsum = nullptr;
-    if (cudaMalloc(&d_colsum, sizeof(float) * static_cast<size_t>(A->num_cols)) != cudaSuccess) {
+    double* d_colsum = nullptr;
+    if (cudaMalloc(&d_colsum, sizeof(double) * static_cast<size_t>(A->num_cols)) != cudaSuccess) {
         cudaGetLastError();
         return static_cast<int>(SpMVError::CUDA_MALLOC);
     }
-    cudaMemsetAsync(d_colsum, 0, sizeof(float) * static_cast<size_t>(A->num_cols), stream);
+    cudaMemsetAsync(d_colsum, 0, sizeof(double) * static_cast<size_t>(A->num_cols), stream);
     cudaError_t e = launch_colsum(view_of(A), d_colsum, stream);
     divide_by_colsum_kernel<<<grid_for(A->nnz), kBlock, 0, stream>>>(A->nnz, A->num_cols, A->d_col_indices, d_colsum,
                                                                      A->d_values);

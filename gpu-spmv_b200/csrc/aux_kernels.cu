@@ -17,20 +17,26 @@ inline unsigned grid_for(long long n, int per_block = kBlock, unsigned cap = 148
     return static_cast<unsigned>(b < cap ? b : cap);
 }
 
-// d_colsum[c] += values[j] for every stored entry (find_dangling_nodes,
-// reference src/pagerank.cu:30-40, evaluated with fp32 atomics)
+// d_colsum[c] += values[j] for every stored entry (find_dangling_nodes, reference
+// src/pagerank.cu:30-40).  The sums are accumulated in f64: an fp32 value enters an f64 sum without
+// rounding as long as the column's partial sums fit 53 bits, which holds for every column of a
+// column-normalised adjacency matrix (k copies of 1/k) and for any column whose entries span
+// less than 2^29 in magnitude -- and a sum that is never rounded does not depend on the order of
+// the atomics.  So the set of dangling nodes (sum == 0) is deterministic, and it is the TRUE
+// cancellation set; the reference's sequential fp32 sum can differ from it only for mixed-sign
+// columns whose fp32 partial sums round (documented in DESIGN.md section 5).
 __global__ void colsum_kernel(int nnz, int cols, const int* __restrict__ col_indices,
-                              const float* __restrict__ values, float* __restrict__ colsum) {
+                              const float* __restrict__ values, double* __restrict__ colsum) {
     for (long long j = blockIdx.x * static_cast<long long>(kBlock) + threadIdx.x; j < nnz;
          j += static_cast<long long>(gridDim.x) * kBlock) {
         const int c = dev::ld_stream_i(col_indices + j);
-        if (c >= 0 && c < cols) atomicAdd(colsum + c, dev::ld_stream_f(values + j));
+        if (c >= 0 && c < cols) atomicAdd(colsum + c, static_cast<double>(dev::ld_stream_f(values + j)));
     }
 }
 
-// bit c = (colsum[c] == 0.0f), reference src/pagerank.cu:42-46
+// bit c = (colsum[c] == 0), reference src/pagerank.cu:42-46
 // (nodes at or beyond valid_cols have no column and are never dangling)
-__global__ void dangling_bits_kernel(const float* __restrict__ colsum, int n, int valid_cols,
+__global__ void dangling_bits_kernel(const double* __restrict__ colsum, int n, int valid_cols,
                                      uint32_t* __restrict__ bits) {
     const int words = (n + 31) / 32;
     for (int w = blockIdx.x * kBlock + threadIdx.x; w < words; w += gridDim.x * kBlock) {
@@ -38,7 +44,7 @@ __global__ void dangling_bits_kernel(const float* __restrict__ colsum, int n, in
         const int lim = min(32, n - w * 32);
         for (int b = 0; b < lim; ++b) {
             const int c = w * 32 + b;
-            m |= ((c < valid_cols && colsum[c] == 0.0f) ? 1u : 0u) << b;
+            m |= ((c < valid_cols && static_cast<float>(colsum[c]) == 0.0f) ? 1u : 0u) << b;
         }
         bits[w] = m;
     }
@@ -139,14 +145,14 @@ __global__ void max_row_len_kernel(int rows, const int* __restrict__ row_ptrs, i
 
 }  // namespace
 
-cudaError_t launch_colsum(const CsrView& A, float* d_colsum, cudaStream_t stream) {
+cudaError_t launch_colsum(const CsrView& A, double* d_colsum, cudaStream_t stream) {
     if (A.nnz <= 0) return cudaSuccess;
     colsum_kernel<<<grid_for(A.nnz), kBlock, 0, stream>>>(A.nnz, A.cols, A.col_indices, A.values, d_colsum);
     count_launches(1);
     return cudaGetLastError();
 }
 
-cudaError_t launch_dangling_bits(const float* d_colsum, int n, int valid_cols, uint32_t* d_bits,
+cudaError_t launch_dangling_bits(const double* d_colsum, int n, int valid_cols, uint32_t* d_bits,
                                  cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     dangling_bits_kernel<<<grid_for((n + 31) / 32), kBlock, 0, stream>>>(d_colsum, n, valid_cols, d_bits);

@@ -5,6 +5,7 @@
 #include "spmv_b200.h"
 
 #include "internal.hpp"
+#include "pagerank_dist.hpp"
 
 #include <cstring>
 #include <new>
@@ -193,6 +194,21 @@ int spmv_b200_spmv_csr_async(const spmv_b200_csr* A, const float* d_x, float* d_
 }
 int spmv_b200_spmv_ell_async(const spmv_b200_ell* A, const float* d_x, float* d_y, void* stream) {
     return guarded([&] { return b200::spmv_ell_async(cpp(A), d_x, d_y, static_cast<cudaStream_t>(stream)); });
+}
+
+int spmv_b200_ell_host_plan_create(const spmv_b200_ell* A, int chunks, spmv_b200_ell_host_plan** out) {
+    return guarded([&] { return b200::ell_host_plan_create(cpp(A), chunks, reinterpret_cast<b200::EllHostPlan**>(out)); });
+}
+void spmv_b200_ell_host_plan_destroy(spmv_b200_ell_host_plan* plan) {
+    b200::ell_host_plan_destroy(reinterpret_cast<b200::EllHostPlan*>(plan));
+}
+int spmv_b200_spmv_ell_host(spmv_b200_ell_host_plan* plan, const float* x_host, float* y_host) {
+    return guarded([&] { return b200::spmv_ell_host(reinterpret_cast<b200::EllHostPlan*>(plan), x_host, y_host); });
+}
+int spmv_b200_ell_host_plan_info(const spmv_b200_ell_host_plan* plan, int* chunks, int* ranged, int* max_lookahead) {
+    if (!plan) return kBadArg;
+    b200::ell_host_plan_info(reinterpret_cast<const b200::EllHostPlan*>(plan), chunks, ranged, max_lookahead);
+    return 0;
 }
 
 // ---- D. bandwidth / PageRank / benchmark ------------------------------------------------
@@ -402,6 +418,8 @@ int spmv_b200_csr_auto_plan_info(const spmv_b200_csr* A, int* hot_columns, long 
     b200::auto_plan_info(cpp(A), hot_columns, hot_nnz);
     return 0;
 }
+void spmv_b200_set_auto_plan(int enabled) { b200::set_auto_plan(enabled != 0); }
+int spmv_b200_auto_plan_enabled(void) { return b200::auto_plan_enabled() ? 1 : 0; }
 void spmv_b200_csr_forget_plan(const spmv_b200_csr* A) {
     if (A) b200::forget_device_csr(cpp(A)->d_col_indices);
 }
@@ -422,13 +440,13 @@ int spmv_b200_pr_plan_create(const spmv_b200_csr* shard, int row_offset, int n_g
 }
 void spmv_b200_pr_plan_destroy(spmv_b200_pr_plan* plan) { b200::pr_plan_destroy(reinterpret_cast<b200::PrPlan*>(plan)); }
 
-int spmv_b200_pr_colsum(const spmv_b200_pr_plan* plan, float* d_colsum, void* stream) {
+int spmv_b200_pr_colsum(const spmv_b200_pr_plan* plan, double* d_colsum, void* stream) {
     if (!plan || !d_colsum) return kBadArg;
     const cudaError_t e = b200::launch_colsum(b200::pr_plan_view(reinterpret_cast<const b200::PrPlan*>(plan)), d_colsum,
                                               static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : SPMV_B200_KERNEL_LAUNCH;
 }
-int spmv_b200_pr_dangling_bits(const float* d_colsum, int n, uint32_t* d_bits, void* stream) {
+int spmv_b200_pr_dangling_bits(const double* d_colsum, int n, uint32_t* d_bits, void* stream) {
     if (!d_colsum || !d_bits || n < 0) return kBadArg;
     return b200::launch_dangling_bits(d_colsum, n, n, d_bits, static_cast<cudaStream_t>(stream)) == cudaSuccess
                ? 0 : SPMV_B200_KERNEL_LAUNCH;
@@ -531,3 +549,57 @@ int spmv_b200_pagerank_device(const spmv_b200_csr* adj, const spmv_b200_pagerank
 }
 
 }  // extern "C"
+
+// ---- multi-GPU PageRank ---------------------------------------------------------------------
+static_assert(sizeof(spmv_b200_pr_dist_result) == sizeof(b200::PrDistResult) &&
+              offsetof(spmv_b200_pr_dist_result, device_seconds) == offsetof(b200::PrDistResult, device_seconds) &&
+              offsetof(spmv_b200_pr_dist_result, kernels_per_iteration) == offsetof(b200::PrDistResult, kernels_per_iteration),
+              "pr_dist result");
+
+int spmv_b200_pagerank_multi(const spmv_b200_csr* adj, const spmv_b200_pagerank_config* config, int n_gpus,
+                             const int* devices, int exchange, int row_weight, int fixed_iterations, float* ranks_out,
+                             spmv_b200_pr_dist_result* out) {
+    return guarded([&] {
+        return b200::pagerank_multi(cpp(adj), cpp(config), n_gpus, devices, exchange, row_weight, fixed_iterations,
+                                    ranks_out, reinterpret_cast<b200::PrDistResult*>(out));
+    });
+}
+int spmv_b200_comm_create(int rank, int world, const char* session, int timeout_s, spmv_b200_comm** out) {
+    return guarded([&] {
+        b200::Comm* c = nullptr;
+        if (!out || b200::comm_create_socket(rank, world, session, timeout_s, &c) != 0) return kBadArg;
+        *out = reinterpret_cast<spmv_b200_comm*>(c);
+        return 0;
+    });
+}
+void spmv_b200_comm_destroy(spmv_b200_comm* comm) { delete reinterpret_cast<b200::Comm*>(comm); }
+int spmv_b200_comm_barrier(spmv_b200_comm* comm) {
+    return comm ? (reinterpret_cast<b200::Comm*>(comm)->barrier() == 0 ? 0 : SPMV_B200_FILE_IO) : kBadArg;
+}
+int spmv_b200_comm_allgather(spmv_b200_comm* comm, const void* send, void* recv, size_t bytes) {
+    if (!comm || !send || !recv) return kBadArg;
+    return reinterpret_cast<b200::Comm*>(comm)->allgather(send, recv, bytes) == 0 ? 0 : SPMV_B200_FILE_IO;
+}
+int spmv_b200_comm_allgather_fds(spmv_b200_comm* comm, int my_fd, int* fds_out) {
+    if (!comm || !fds_out || my_fd < 0) return kBadArg;
+    return reinterpret_cast<b200::Comm*>(comm)->allgather_fds(my_fd, fds_out) == 0 ? 0 : SPMV_B200_FILE_IO;
+}
+int spmv_b200_pr_dist_create(spmv_b200_comm* comm, const spmv_b200_csr* shard, int row_offset, int n_global, int exchange,
+                             spmv_b200_pr_dist** out) {
+    return guarded([&] {
+        return b200::pr_dist_create(reinterpret_cast<b200::Comm*>(comm), cpp(shard), row_offset, n_global, exchange,
+                                    reinterpret_cast<b200::PrDist**>(out));
+    });
+}
+int spmv_b200_pr_dist_run(spmv_b200_pr_dist* d, const spmv_b200_pagerank_config* config, int fixed_iterations,
+                          spmv_b200_pr_dist_result* out) {
+    return guarded([&] {
+        return b200::pr_dist_run(reinterpret_cast<b200::PrDist*>(d), cpp(config), fixed_iterations,
+                                 reinterpret_cast<b200::PrDistResult*>(out));
+    });
+}
+const float* spmv_b200_pr_dist_ranks(const spmv_b200_pr_dist* d) { return b200::pr_dist_ranks(reinterpret_cast<const b200::PrDist*>(d)); }
+int spmv_b200_pr_dist_exchange(const spmv_b200_pr_dist* d) { return b200::pr_dist_exchange(reinterpret_cast<const b200::PrDist*>(d)); }
+int spmv_b200_pr_dist_hub_columns(const spmv_b200_pr_dist* d) { return b200::pr_dist_hub_columns(reinterpret_cast<const b200::PrDist*>(d)); }
+void spmv_b200_pr_dist_destroy(spmv_b200_pr_dist* d) { b200::pr_dist_destroy(reinterpret_cast<b200::PrDist*>(d)); }
+int spmv_b200_nccl_available(void) { return b200::nccl_available() ? 1 : 0; }

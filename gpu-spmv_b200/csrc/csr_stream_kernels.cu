@@ -487,6 +487,157 @@ csr_pipe_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// csr_prod_kernel -- SCALAR_CSR / one-lane VECTOR_CSR for matrices of SHORT rows: the same
+// persistent TMA ring as csr_pipe_kernel (row_ptrs window + aligned value / column spans per stage),
+// but the window is consumed in two coalesced phases instead of by row owners walking their rows:
+//
+//   1. products IN PLACE, in stream order: thread t takes staged slots t, t + 256, ... and overwrites
+//      the value slot with value * x[col] (__fmul_rn).  Consecutive lanes read consecutive slots (no
+//      bank conflicts, no per-element bounds: every staged slot is a real non-zero of the matrix) and
+//      their x gathers touch neighbouring columns of neighbouring rows;
+//   2. after one barrier, thread r sums the products of row r front to back (__fadd_rn).
+//
+// Per row this is exactly spmv_cpu_csr's `sum += values[j] * x[col[j]]` with separately rounded
+// multiply and add (reference src/spmv_cpu.cpp:6-16) => bit-identical, like csr_pipe_kernel<1>.
+// Why: ncu of csr_pipe_kernel<1,6,false> on config 2 (profiles/r1_csr_pipe_c2.md) showed it
+// issue-bound -- 45 thread instructions per non-zero, three predicates per element -- with DRAM at
+// 63 %.  Here a non-zero costs ~7 instructions in phase 1 and ~5 in phase 2.
+// Non-zeros that are not staged (the last nnz % 4 of the matrix, or a window that exceeds the stage)
+// are multiplied from global memory by the row that owns them, in the same order.
+constexpr int kProdBatch = 8;  // gathers in flight per thread
+
+__global__ void __launch_bounds__(kThreads)
+csr_prod_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* __restrict__ col_indices,
+                const float* __restrict__ values, const float* __restrict__ x, float* __restrict__ y,
+                int window_rows, int rows_per_thread, int cap, int stages) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [stages] (<= 16)
+    unsigned char* ring = smem_raw + 128;
+    const size_t stage_bytes = sizeof(PipeStageHeader) + static_cast<size_t>(window_rows + 4) * 4 +
+                               static_cast<size_t>(cap) * 8;
+    const int tid = threadIdx.x;
+    const int num_windows = (rows + window_rows - 1) / window_rows;
+
+    auto stage_header = [&](int s) { return reinterpret_cast<PipeStageHeader*>(ring + s * stage_bytes); };
+    auto stage_rp = [&](int s) { return reinterpret_cast<int*>(ring + s * stage_bytes + sizeof(PipeStageHeader)); };
+    auto stage_val = [&](int s) { return reinterpret_cast<float*>(stage_rp(s) + window_rows + 4); };
+    auto stage_col = [&](int s) { return reinterpret_cast<int*>(stage_val(s) + cap); };
+
+    auto issue = [&](int w, int s, int n0, int n1) {  // thread 0 only
+        const int r0 = w * window_rows;
+        const int base = n0 & ~3;
+        int end = min((n1 + 3) & ~3, nnz & ~3);
+        end = min(end, base + cap);
+        end = max(end, base);
+        const bool rp_ok = r0 + window_rows + 4 <= rows + 1;
+        PipeStageHeader* h = stage_header(s);
+        h->base = base;
+        h->staged_end = end;
+        h->rp_staged = rp_ok ? 1 : 0;
+        h->overflow = 0;
+        const uint32_t nz_bytes = static_cast<uint32_t>(end - base) * 4u;
+        const uint32_t rp_bytes = rp_ok ? static_cast<uint32_t>(window_rows + 4) * 4u : 0u;
+        dev::mbar_arrive_expect_tx(bars + s, 2u * nz_bytes + rp_bytes);
+        if (rp_bytes) dev::tma_bulk_g2s(stage_rp(s), row_ptrs + r0, rp_bytes, bars + s);
+        if (nz_bytes) {
+            dev::tma_bulk_g2s(stage_val(s), values + base, nz_bytes, bars + s);
+            dev::tma_bulk_g2s(stage_col(s), col_indices + base, nz_bytes, bars + s);
+        }
+    };
+    auto window_bounds = [&](int w, int& n0, int& n1) {
+        const int r0 = w * window_rows;
+        n0 = __ldg(row_ptrs + r0);
+        n1 = __ldg(row_ptrs + min(r0 + window_rows, rows));
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) dev::mbar_init(bars + s, 1);
+        dev::mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            const int w = blockIdx.x + s * gridDim.x;
+            if (w < num_windows) {
+                int n0, n1;
+                window_bounds(w, n0, n1);
+                issue(w, s, n0, n1);
+            }
+        }
+    }
+
+    int it = 0;
+    for (int w = blockIdx.x; w < num_windows; w += gridDim.x, ++it) {
+        const int s = it % stages;
+        const uint32_t parity = (it / stages) & 1u;
+        const int next = w + stages * gridDim.x;
+        int next_n0 = 0, next_n1 = 0;
+        if (tid == 0 && next < num_windows) window_bounds(next, next_n0, next_n1);  // latency hidden by the consume phase
+
+        dev::mbar_wait(bars + s, parity);
+        const PipeStageHeader h = *stage_header(s);
+        int* s_rp = stage_rp(s);
+        float* s_val = stage_val(s);
+        const int* s_col = stage_col(s);
+        const int r0 = w * window_rows;
+        const int nr = min(window_rows, rows - r0);
+        if (!h.rp_staged) {  // last window(s): a bulk copy of window_rows + 4 entries would over-read
+            for (int i = tid; i <= nr; i += kThreads) s_rp[i] = __ldg(row_ptrs + r0 + i);
+        }
+
+        // ---- phase 1: products in place, stream order ------------------------------------------
+        // every gather of a batch is issued before the first product: one gather latency per window
+        const int n_staged = h.staged_end - h.base;
+        for (int j0 = tid; j0 < n_staged; j0 += kProdBatch * kThreads) {
+            int c[kProdBatch];
+            float xv[kProdBatch];
+#pragma unroll
+            for (int u = 0; u < kProdBatch; ++u) {
+                const int j = j0 + u * kThreads;
+                if (j < n_staged) c[u] = s_col[j];
+            }
+#pragma unroll
+            for (int u = 0; u < kProdBatch; ++u) {
+                const int j = j0 + u * kThreads;
+                if (j < n_staged) xv[u] = dev::ld_x(x + c[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kProdBatch; ++u) {
+                const int j = j0 + u * kThreads;
+                if (j < n_staged) s_val[j] = __fmul_rn(s_val[j], xv[u]);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: one thread per row, front to back ----------------------------------------
+        const float* s_prod = s_val - h.base;  // s_prod[j] for a global non-zero index j
+        for (int i = 0; i < rows_per_thread; ++i) {
+            const int r = tid + i * kThreads;
+            if (r < nr) {
+                const int a = s_rp[r], b = s_rp[r + 1];
+                float acc = 0.0f;
+                if (b <= h.staged_end && a >= h.base) {
+                    for (int j = a; j < b; ++j) acc = __fadd_rn(acc, s_prod[j]);
+                } else {  // part of the row was not staged (matrix tail / oversized window)
+                    for (int j = a; j < b; ++j) {
+                        const float p = (j >= h.base && j < h.staged_end)
+                                            ? s_prod[j]
+                                            : __fmul_rn(dev::ld_stream_f(values + j), dev::ld_x(x + dev::ld_stream_i(col_indices + j)));
+                        acc = __fadd_rn(acc, p);
+                    }
+                }
+                y[r0 + r] = acc;
+            }
+        }
+        __syncthreads();  // stage s is free again
+        if (tid == 0 && next < num_windows) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(next, s, next_n0, next_n1);
+        }
+    }
+}
+
 int stream_env_int(const char* name, int fallback) {
     const char* v = getenv(name);
     return v ? atoi(v) : fallback;
@@ -522,6 +673,11 @@ int longest_row_cached(const CsrView& A, cudaStream_t stream) {
         auto it = cache.find(key);
         if (it != cache.end()) return it->second;
     }
+    // the measurement below synchronises the stream, which would invalidate an ongoing capture: while
+    // capturing, an unknown matrix takes the robust kernel (correct for any row length) and is not cached
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &capturing) != cudaSuccess) cudaGetLastError();
+    if (capturing != cudaStreamCaptureStatusNone) return 0x7fffffff;
     int* d_max = nullptr;
     int longest = 0x7fffffff;  // unknown -> robust kernel
     if (cudaMalloc(&d_max, sizeof(int)) == cudaSuccess) {
@@ -599,6 +755,58 @@ cudaError_t launch_pipe_lpr(const CsrView& A, const float* x, float* y, cudaStre
     return launch_pipe_lpr_u<LPR, 8, false>(A, x, y, stream);
 }
 
+// Geometry of csr_prod_kernel: windows of 256 * rpt rows holding ~1.3-2.5 K non-zeros.
+void prod_geometry(const CsrView& A, int& rpt, int& cap) {
+    const double avg = static_cast<double>(A.nnz) / A.rows;
+    static const int env_nz = stream_env_int("SPMV_B200_CSR_PROD_WINDOW_NNZ", 1536);
+    rpt = static_cast<int>(env_nz / (avg * kThreads) + 0.5);
+    rpt = rpt < 1 ? 1 : (rpt > 8 ? 8 : rpt);
+    const int window = kThreads * rpt;
+    cap = static_cast<int>(1.125 * avg * window) + 32;
+    cap = (cap + 127) / 128 * 128;
+}
+
+cudaError_t launch_prod(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
+    int rpt, cap;
+    prod_geometry(A, rpt, cap);
+    const int window = kThreads * rpt;
+    static const int env_stages = stream_env_int("SPMV_B200_CSR_STAGES", 0);
+    static const int env_ctas = stream_env_int("SPMV_B200_CSR_CTAS_PER_SM", 0);
+    const int stages = env_stages > 1 ? (env_stages > 16 ? 16 : env_stages) : 2;
+    const size_t stage_bytes = sizeof(PipeStageHeader) + static_cast<size_t>(window + 4) * 4 + static_cast<size_t>(cap) * 8;
+    const size_t smem = 128 + stages * stage_bytes;
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // caller falls back
+    cudaError_t e = cudaFuncSetAttribute(csr_prod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    int fit = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, csr_prod_kernel, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (fit < 1) return cudaErrorInvalidConfiguration;
+    const int ctas_per_sm = (env_ctas > 0 && env_ctas < fit) ? env_ctas : fit;
+    int sms = 148, dev_id = 0;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    const int num_windows = (A.rows + window - 1) / window;
+    int blocks = sms * ctas_per_sm;
+    if (blocks > num_windows) blocks = num_windows;
+    csr_prod_kernel<<<blocks, kThreads, smem, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values, x, y, window, rpt,
+                                                        cap, stages);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+// Short rows only: thread r walks row r alone in phase 2, and a window must fit a stage.
+bool prod_eligible(const CsrView& A, cudaStream_t stream) {
+    static const int mode = stream_env_int("SPMV_B200_CSR_PROD", -1);  // 0 off, 1 forced, -1 by structure
+    if (mode == 0) return false;
+    if (mode == 1) return true;
+    const double avg = static_cast<double>(A.nnz) / A.rows;
+    if (avg > 24.0) return false;
+    int rpt, cap;
+    prod_geometry(A, rpt, cap);
+    return longest_row_cached(A, stream) <= 64;
+}
+
 bool pipe_eligible(const CsrView& A) {
     static const int disable = stream_env_int("SPMV_B200_CSR_NO_PIPE", 0);
     const uintptr_t bits = reinterpret_cast<uintptr_t>(A.values) | reinterpret_cast<uintptr_t>(A.col_indices) |
@@ -609,6 +817,10 @@ bool pipe_eligible(const CsrView& A) {
 template <int LPR>
 cudaError_t launch_best_lpr(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
     if (pipe_eligible(A)) {
+        if (LPR == 1 && prod_eligible(A, stream)) {
+            const cudaError_t e = launch_prod(A, x, y, stream);
+            if (e != cudaErrorInvalidConfiguration) return e;
+        }
         const cudaError_t e = launch_pipe_lpr<LPR>(A, x, y, stream);
         if (e != cudaErrorInvalidConfiguration) return e;
     }

@@ -240,11 +240,20 @@ int csr_plan_refresh_values(CsrPlan* p, cudaStream_t stream) {
     return 0;
 }
 
-// Automatic plans for spmv_csr(MERGE_PATH): only for device arrays uploaded by csr_to_gpu (the
-// library allocated them and sees them freed), built on the second merge-path call over the same
-// arrays.  Only col_indices is re-encoded; values and x are read live.  A caller that overwrites
-// d_col_indices of such an upload IN PLACE must call spmv_b200_csr_forget_plan.
+// Automatic plans for spmv_csr(MERGE_PATH) -- OPT-IN (spmv_b200_set_auto_plan(1) or
+// SPMV_B200_AUTO_PLAN=1; off by default).  A plan holds a private re-encoding of col_indices and,
+// for the segmented-stream kernel, of the row structure of row_ptrs; values and x are read live.
+// The reference's struct fields are public, so a caller may legally rewrite d_col_indices /
+// d_row_ptrs in place (or cudaFree them and get the same address back for another matrix of the
+// same shape): with a plan attached that would silently multiply by the OLD sparsity pattern.  A
+// drop-in must not change results by default, hence the opt-in; a caller that switches it on
+// promises to call spmv_b200_csr_forget_plan after such an edit.  When on: only
+// device arrays uploaded by csr_to_gpu / csr_from_coo_device are planned (the library sees them
+// freed), on the second merge-path call over the same arrays; the plan costs 4 bytes per non-zero
+// of device memory (+ 4 per non-empty row for the segmented stream).
 namespace {
+std::atomic<int> g_auto_plan_enabled{-1};  // -1: read SPMV_B200_AUTO_PLAN on first use
+
 struct AutoEntry {
     int rows = 0, nnz = 0;
     int calls = 0;
@@ -263,8 +272,19 @@ int hot_env_mode() {
 }
 }  // namespace
 
+bool auto_plan_enabled() {
+    int v = g_auto_plan_enabled.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("SPMV_B200_AUTO_PLAN");
+        v = (e && atoi(e) > 0) ? 1 : 0;
+        g_auto_plan_enabled.store(v, std::memory_order_relaxed);
+    }
+    return v > 0;
+}
+void set_auto_plan(bool on) { g_auto_plan_enabled.store(on ? 1 : 0, std::memory_order_relaxed); }
+
 void note_device_csr(const CSRMatrix* A) {
-    if (!A || !A->d_col_indices || hot_env_mode() == 0) return;
+    if (!A || !A->d_col_indices || hot_env_mode() == 0) return;  // registered even while auto-plans are off: cheap, and the switch may come later
     std::lock_guard<std::mutex> lock(g_auto_mu);
     AutoEntry*& e = g_auto[A->d_col_indices];
     if (e) {
@@ -301,7 +321,7 @@ void auto_plan_info(const CSRMatrix* A, int* hot_columns, long long* hot_nnz) {
 
 // nullptr: no plan (not an upload of ours, first call, or not worthwhile)
 static const PlannedCsr* auto_planned(const CSRMatrix* A, cudaStream_t stream) {
-    if (hot_env_mode() == 0 || !A->d_col_indices) return nullptr;
+    if (hot_env_mode() == 0 || !A->d_col_indices || !auto_plan_enabled()) return nullptr;
     std::lock_guard<std::mutex> lock(g_auto_mu);
     auto it = g_auto.find(A->d_col_indices);
     if (it == g_auto.end()) return nullptr;

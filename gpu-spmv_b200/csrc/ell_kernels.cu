@@ -247,7 +247,9 @@ template <int RPT>
 __global__ void __launch_bounds__(kEllThreads)
 ell_tma_pipe_kernel(int rows, int width, int stages, const int* __restrict__ col_indices,
                     const float* __restrict__ values, const float* __restrict__ x, float* __restrict__ y,
-                    unsigned long long* __restrict__ nnz_counter) {
+                    unsigned long long* __restrict__ nnz_counter, int row_lo, int row_hi) {
+    // rows = slot stride of the column-major arrays (the whole matrix); this launch covers rows
+    // [row_lo, row_hi) (the whole matrix, or one row chunk of the pipelined host-buffer call)
     constexpr int kWindow = RPT * kEllThreads;
     extern __shared__ __align__(16) unsigned char ell_smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(ell_smem);              // [stages] (<= 16)
@@ -256,11 +258,11 @@ ell_tma_pipe_kernel(int rows, int width, int stages, const int* __restrict__ col
 
     const int tid = threadIdx.x;
     const size_t stride = static_cast<size_t>(rows);
-    const int num_windows = static_cast<int>((static_cast<long long>(rows) + kWindow - 1) / kWindow);
+    const int num_windows = static_cast<int>((static_cast<long long>(row_hi - row_lo) + kWindow - 1) / kWindow);
 
     auto issue = [&](int window, int stage) {  // thread 0 only
-        const long long r0 = static_cast<long long>(window) * kWindow;
-        const int nr = static_cast<int>(min(static_cast<long long>(kWindow), rows - r0));
+        const long long r0 = row_lo + static_cast<long long>(window) * kWindow;
+        const int nr = static_cast<int>(min(static_cast<long long>(kWindow), row_hi - r0));
         const uint32_t slice_bytes = static_cast<uint32_t>(nr) * sizeof(float);
         float* s_val = reinterpret_cast<float*>(buffers + stage * stage_bytes);
         int* s_col = reinterpret_cast<int*>(s_val + width * kWindow);
@@ -289,8 +291,8 @@ ell_tma_pipe_kernel(int rows, int width, int stages, const int* __restrict__ col
     for (int w = blockIdx.x; w < num_windows; w += gridDim.x, ++it) {
         const int stage = it % stages;
         const uint32_t parity = (it / stages) & 1u;
-        const long long r0 = static_cast<long long>(w) * kWindow;
-        const int nr = static_cast<int>(min(static_cast<long long>(kWindow), rows - r0));
+        const long long r0 = row_lo + static_cast<long long>(w) * kWindow;
+        const int nr = static_cast<int>(min(static_cast<long long>(kWindow), row_hi - r0));
         const float* s_val = reinterpret_cast<const float*>(buffers + stage * stage_bytes);
         const int* s_col = reinterpret_cast<const int*>(s_val + width * kWindow);
         dev::mbar_wait(bars + stage, parity);
@@ -332,7 +334,8 @@ int env_int(const char* name, int fallback) {
 
 template <int RPT>
 cudaError_t launch_tma_pipe(int rows, int width, const int* ci, const float* va, const float* x, float* y,
-                            unsigned long long* counter, cudaStream_t stream) {
+                            unsigned long long* counter, cudaStream_t stream, int row_lo = 0, int row_hi = -1) {
+    if (row_hi < 0) row_hi = rows;
     constexpr int kWindow = RPT * kEllThreads;
     static const int env_stages = env_int("SPMV_B200_ELL_STAGES", 0);
     static const int env_ctas = env_int("SPMV_B200_ELL_CTAS_PER_SM", 0);
@@ -355,10 +358,12 @@ cudaError_t launch_tma_pipe(int rows, int width, const int* ci, const float* va,
     int sms = 148, dev_id = 0;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
-    const int num_windows = static_cast<int>((static_cast<long long>(rows) + kWindow - 1) / kWindow);
+    const int num_windows = static_cast<int>((static_cast<long long>(row_hi - row_lo) + kWindow - 1) / kWindow);
+    if (num_windows <= 0) return cudaSuccess;
     int blocks = sms * ctas_per_sm;
     if (blocks > num_windows) blocks = num_windows;
-    ell_tma_pipe_kernel<RPT><<<blocks, kEllThreads, smem, stream>>>(rows, width, stages, ci, va, x, y, counter);
+    ell_tma_pipe_kernel<RPT><<<blocks, kEllThreads, smem, stream>>>(rows, width, stages, ci, va, x, y, counter, row_lo,
+                                                                    row_hi);
     count_launches(1);
     return cudaGetLastError();
 }
@@ -398,6 +403,17 @@ cudaError_t launch_ell(int rows, int width, const int* col_indices, const float*
     if (rows % 2 == 0 && all_aligned(col_indices, values, y, 8))
         return launch_rpt<2>(rows, width, col_indices, values, x, y, nnz_counter, stream);
     return launch_rpt<1>(rows, width, col_indices, values, x, y, nnz_counter, stream);
+}
+
+// Rows [row_lo, row_hi) of the product only (row_lo % 4 == 0): one row chunk of the pipelined
+// host-buffer call (host_pipeline.cu).  cudaErrorInvalidConfiguration: the matrix does not qualify
+// for the TMA pipeline (alignment / width) -- the caller then multiplies the whole matrix at once.
+cudaError_t launch_ell_rows(int rows, int width, const int* col_indices, const float* values, const float* x, float* y,
+                            int row_lo, int row_hi, cudaStream_t stream) {
+    if (rows <= 0 || row_hi <= row_lo) return cudaSuccess;
+    if (width <= 0 || width > 8 || rows % 4 != 0 || row_lo % 4 != 0 || !all_aligned(col_indices, values, y, 16))
+        return cudaErrorInvalidConfiguration;
+    return launch_tma_pipe<1>(rows, width, col_indices, values, x, y, nullptr, stream, row_lo, row_hi);
 }
 
 }  // namespace b200

@@ -1,0 +1,192 @@
+// host_pipeline.cu -- y_host = A * x_host for an ELL matrix that is resident in HBM while the
+// vectors live in HOST memory: the end-to-end form of the hot path (what a caller of the reference
+// does around spmv_ell: cudaMemcpy x up, spmv_ell, cudaMemcpy y down -- reference README.md:98-118,
+// src/benchmark.cu:36-38,95-102).  Done serially that is H2D + kernel + D2H; the kernel is 5 % of it.
+//
+// Here the three legs are pipelined over row chunks on three streams:
+//     copy stream    x chunk 0, 1, 2, ...                      (H2D, PCIe down-link)
+//     compute stream rows of chunk c as soon as the x entries THEY read have arrived
+//     drain stream   y chunk c as soon as chunk c is computed  (D2H, PCIe up-link)
+// Which x entries a row chunk reads is a property of the matrix, measured once per plan on the
+// device: the column range [min col, max col] of every row chunk.  A banded matrix (BASELINE
+// config 2: the 5-point Laplacian reads x[i - 4096 .. i + 4096]) then overlaps the up- and
+// down-link almost completely (PCIe is full duplex); a matrix whose rows read all of x
+// degenerates to H2D, then compute overlapped with D2H -- never worse than the serial form.
+// Numerics: the row chunks run the same ELL kernel (ell_tma_pipe_kernel<1>) on the same rows, so
+// y is bit-identical to spmv_ell / spmv_cpu_ell.
+#include "internal.hpp"
+
+#include <algorithm>
+#include <climits>
+#include <new>
+#include <vector>
+
+namespace spmv {
+namespace b200 {
+
+cudaError_t launch_ell_rows(int rows, int width, const int* col_indices, const float* values, const float* x, float* y,
+                            int row_lo, int row_hi, cudaStream_t stream);
+
+namespace {
+
+// min / max column (padding excluded) of every row chunk; chunk c = rows [c * chunk_rows, ...)
+__global__ void ell_chunk_col_range_kernel(int rows, int width, const int* __restrict__ col_indices, int chunk_rows,
+                                           int* __restrict__ cmin, int* __restrict__ cmax) {
+    const long long total = static_cast<long long>(rows) * width;
+    int lo = INT_MAX, hi = -1, mine = -1;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int row = static_cast<int>(i % rows);
+        const int chunk = row / chunk_rows;
+        if (chunk != mine) {
+            if (mine >= 0 && hi >= 0) { atomicMin(cmin + mine, lo); atomicMax(cmax + mine, hi); }
+            mine = chunk; lo = INT_MAX; hi = -1;
+        }
+        const int c = col_indices[i];
+        if (c >= 0) { lo = min(lo, c); hi = max(hi, c); }
+    }
+    if (mine >= 0 && hi >= 0) { atomicMin(cmin + mine, lo); atomicMax(cmax + mine, hi); }
+}
+
+}  // namespace
+
+struct EllHostPlan {
+    int rows = 0, cols = 0, width = 0;
+    const int* d_cols = nullptr;      // the matrix (borrowed: must outlive the plan)
+    const float* d_vals = nullptr;
+    int chunks = 0, chunk_rows = 0;   // row chunks
+    int x_chunks = 0, x_chunk = 0;    // x chunks (entries)
+    std::vector<int> need;            // last x chunk a row chunk reads (-1: none)
+    bool ranged = false;              // the row-range kernel applies; else one launch after all of x
+    float* d_x = nullptr;
+    float* d_y = nullptr;
+    cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
+    std::vector<cudaEvent_t> ev_x, ev_y;
+    cudaEvent_t ev_start = nullptr;
+    ~EllHostPlan() {
+        for (auto e : ev_x) cudaEventDestroy(e);
+        for (auto e : ev_y) cudaEventDestroy(e);
+        if (ev_start) cudaEventDestroy(ev_start);
+        if (s_up) cudaStreamDestroy(s_up);
+        if (s_run) cudaStreamDestroy(s_run);
+        if (s_down) cudaStreamDestroy(s_down);
+        cudaFree(d_x);
+        cudaFree(d_y);
+    }
+};
+
+int ell_host_plan_create(const ELLMatrix* A, int chunks, EllHostPlan** out) {
+    if (!A || !out) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
+    if (!A->d_col_indices || !A->d_values) return static_cast<int>(SpMVError::INVALID_FORMAT);
+    EllHostPlan* p = new (std::nothrow) EllHostPlan();
+    if (!p) return static_cast<int>(SpMVError::OUT_OF_MEMORY);
+    p->rows = A->num_rows; p->cols = A->num_cols; p->width = A->max_nnz_per_row;
+    p->d_cols = A->d_col_indices; p->d_vals = A->d_values;
+    if (chunks <= 0) chunks = 8;  // measured on B200 / PCIe Gen5 (config 2): 4 / 8 / 16 / 32 chunks -> 2.02 / 1.85 / 1.89 / 2.19 ms
+    // chunk boundaries on multiples of 1024 rows / entries: TMA slices and copies stay 16-byte aligned
+    auto round_up = [](long long v, long long m) { return (v + m - 1) / m * m; };
+    p->chunk_rows = static_cast<int>(std::max<long long>(1024, round_up((static_cast<long long>(p->rows) + chunks - 1) / chunks, 1024)));
+    p->chunks = p->rows > 0 ? (p->rows + p->chunk_rows - 1) / p->chunk_rows : 0;
+    p->x_chunk = static_cast<int>(std::max<long long>(1024, round_up((static_cast<long long>(p->cols) + chunks - 1) / chunks, 1024)));
+    p->x_chunks = p->cols > 0 ? (p->cols + p->x_chunk - 1) / p->x_chunk : 0;
+    bool ok = cudaMalloc(&p->d_x, sizeof(float) * static_cast<size_t>(std::max(p->cols, 1))) == cudaSuccess &&
+              cudaMalloc(&p->d_y, sizeof(float) * static_cast<size_t>(std::max(p->rows, 1))) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    p->ev_x.assign(p->x_chunks, nullptr);
+    p->ev_y.assign(p->chunks, nullptr);
+    for (auto& e : p->ev_x) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& e : p->ev_y) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    p->need.assign(p->chunks, p->x_chunks - 1);
+    // does the row-range kernel apply to this matrix?  (same test as launch_ell_rows)
+    p->ranged = p->width >= 1 && p->width <= 8 && p->rows % 4 == 0 &&
+                ((reinterpret_cast<uintptr_t>(p->d_cols) | reinterpret_cast<uintptr_t>(p->d_vals)) & 15u) == 0;
+    if (ok && p->ranged && p->chunks > 0 && p->width > 0) {
+        int *d_min = nullptr, *d_max = nullptr;
+        std::vector<int> h_min(p->chunks, INT_MAX), h_max(p->chunks, -1);
+        ok = cudaMalloc(&d_min, sizeof(int) * p->chunks) == cudaSuccess && cudaMalloc(&d_max, sizeof(int) * p->chunks) == cudaSuccess;
+        if (ok) {
+            cudaMemcpy(d_min, h_min.data(), sizeof(int) * p->chunks, cudaMemcpyHostToDevice);
+            cudaMemcpy(d_max, h_max.data(), sizeof(int) * p->chunks, cudaMemcpyHostToDevice);
+            ell_chunk_col_range_kernel<<<148 * 8, 256>>>(p->rows, p->width, p->d_cols, p->chunk_rows, d_min, d_max);
+            count_launches(1);
+            ok = cudaMemcpy(h_min.data(), d_min, sizeof(int) * p->chunks, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                 cudaMemcpy(h_max.data(), d_max, sizeof(int) * p->chunks, cudaMemcpyDeviceToHost) == cudaSuccess;
+            // x chunks are uploaded in index order on one stream, so "the last chunk read" is what a row chunk waits for
+            for (int c = 0; ok && c < p->chunks; ++c) p->need[c] = h_max[c] < 0 ? -1 : std::min(h_max[c], p->cols - 1) / p->x_chunk;
+        }
+        cudaFree(d_min);
+        cudaFree(d_max);
+    }
+    if (!ok) {
+        cudaGetLastError();
+        delete p;
+        return static_cast<int>(SpMVError::CUDA_MALLOC);
+    }
+    *out = p;
+    return 0;
+}
+
+void ell_host_plan_destroy(EllHostPlan* p) { delete p; }
+
+// Blocking: returns when y_host is complete.  x_host / y_host should be page-locked (cudaHostAlloc /
+// cudaHostRegister) for the copies to overlap; pageable memory works but serialises.
+int spmv_ell_host(EllHostPlan* p, const float* x_host, float* y_host) {
+    if (!p || !x_host || !y_host) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
+    if (p->rows <= 0) return 0;
+    bool ok = true;
+    // order after whatever the caller queued on the legacy stream (matrix upload, ...)
+    ok = ok && cudaEventRecord(p->ev_start, nullptr) == cudaSuccess;
+    ok = ok && cudaStreamWaitEvent(p->s_up, p->ev_start, 0) == cudaSuccess;
+    ok = ok && cudaStreamWaitEvent(p->s_run, p->ev_start, 0) == cudaSuccess;
+    for (int j = 0; ok && j < p->x_chunks; ++j) {
+        const size_t lo = static_cast<size_t>(j) * p->x_chunk;
+        const size_t n = std::min<size_t>(p->x_chunk, static_cast<size_t>(p->cols) - lo);
+        ok = cudaMemcpyAsync(p->d_x + lo, x_host + lo, n * sizeof(float), cudaMemcpyHostToDevice, p->s_up) == cudaSuccess &&
+             cudaEventRecord(p->ev_x[j], p->s_up) == cudaSuccess;
+    }
+    if (ok && !p->ranged) {  // one launch over the whole matrix once all of x is there
+        if (p->x_chunks > 0) ok = cudaStreamWaitEvent(p->s_run, p->ev_x[p->x_chunks - 1], 0) == cudaSuccess;
+        ok = ok && launch_ell(p->rows, p->width, p->d_cols, p->d_vals, p->d_x, p->d_y, nullptr, p->s_run) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(y_host, p->d_y, sizeof(float) * static_cast<size_t>(p->rows), cudaMemcpyDeviceToHost, p->s_run) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(p->s_run) == cudaSuccess;
+    } else if (ok) {
+        int waited = -1;  // highest x chunk the compute stream already waits for
+        for (int c = 0; ok && c < p->chunks; ++c) {
+            const int lo = c * p->chunk_rows, hi = std::min(p->rows, lo + p->chunk_rows);
+            if (p->need[c] > waited) {
+                ok = cudaStreamWaitEvent(p->s_run, p->ev_x[p->need[c]], 0) == cudaSuccess;
+                waited = p->need[c];
+            }
+            ok = ok && launch_ell_rows(p->rows, p->width, p->d_cols, p->d_vals, p->d_x, p->d_y, lo, hi, p->s_run) == cudaSuccess;
+            ok = ok && cudaEventRecord(p->ev_y[c], p->s_run) == cudaSuccess;
+            ok = ok && cudaStreamWaitEvent(p->s_down, p->ev_y[c], 0) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(y_host + lo, p->d_y + lo, sizeof(float) * static_cast<size_t>(hi - lo),
+                                       cudaMemcpyDeviceToHost, p->s_down) == cudaSuccess;
+        }
+        ok = ok && cudaStreamSynchronize(p->s_down) == cudaSuccess;
+        ok = cudaStreamSynchronize(p->s_up) == cudaSuccess && ok;  // x chunks no row read (none for a square matrix)
+    }
+    if (!ok) {
+        cudaGetLastError();
+        cudaStreamSynchronize(p->s_up); cudaStreamSynchronize(p->s_run); cudaStreamSynchronize(p->s_down);
+        cudaGetLastError();
+        return static_cast<int>(SpMVError::KERNEL_LAUNCH);
+    }
+    return 0;
+}
+
+void ell_host_plan_info(const EllHostPlan* p, int* chunks, int* ranged, int* max_lookahead) {
+    if (chunks) *chunks = p ? p->chunks : 0;
+    if (ranged) *ranged = p && p->ranged ? 1 : 0;
+    if (max_lookahead) {  // how many x chunks beyond its own index a row chunk waits for, at most
+        int m = 0;
+        if (p) for (int c = 0; c < p->chunks; ++c) m = std::max(m, p->need[c] - c);
+        *max_lookahead = m;
+    }
+}
+
+}  // namespace b200
+}  // namespace spmv

@@ -210,8 +210,8 @@ cudaError_t planned_build(const CsrView& A, PlannedCsr* out, int capacity, bool 
 cudaError_t launch_reduce_partials(const double* partials, int count, double* out, cudaStream_t stream);
 
 // PageRank helpers
-cudaError_t launch_colsum(const CsrView& A, float* d_colsum, cudaStream_t stream);
-cudaError_t launch_dangling_bits(const float* d_colsum, int n, int valid_cols, uint32_t* d_bits,
+cudaError_t launch_colsum(const CsrView& A, double* d_colsum, cudaStream_t stream);  // f64 sums: see aux_kernels.cu
+cudaError_t launch_dangling_bits(const double* d_colsum, int n, int valid_cols, uint32_t* d_bits,
                                  cudaStream_t stream);
 cudaError_t launch_pr_init(int n, const uint32_t* d_bits, float* d_r, float* d_dsum,
                            double* d_tmp, cudaStream_t stream);
@@ -258,11 +258,21 @@ int spmv_csr_planned(const CsrPlan* plan, const float* d_x, float* d_y, cudaStre
 void note_device_csr(const CSRMatrix* A);
 void forget_device_csr(const void* d_col_indices);
 void auto_plan_info(const CSRMatrix* A, int* hot_columns, long long* hot_nnz);
+// automatic plans are opt-in (default off, or SPMV_B200_AUTO_PLAN=1): see dispatch.cu
+bool auto_plan_enabled();
+void set_auto_plan(bool on);
 
 // stream-ordered twins of spmv_csr / spmv_ell (no sync, no timing); return a SpMVError
 int spmv_csr_async(const CSRMatrix* A, const float* d_x, float* d_y, const SpMVConfig* config,
                    cudaStream_t stream);
 int spmv_ell_async(const ELLMatrix* A, const float* d_x, float* d_y, cudaStream_t stream);
+
+// ---- pipelined host-buffer ELL SpMV (host_pipeline.cu) -------------------------------------
+struct EllHostPlan;
+int ell_host_plan_create(const ELLMatrix* A, int chunks, EllHostPlan** out);
+void ell_host_plan_destroy(EllHostPlan* plan);
+int spmv_ell_host(EllHostPlan* plan, const float* x_host, float* y_host);
+void ell_host_plan_info(const EllHostPlan* plan, int* chunks, int* ranged, int* max_lookahead);
 
 // ---- PageRank plan over one row shard (pagerank.cu) -------------------------------------
 struct PrPlan;
@@ -273,6 +283,7 @@ int pr_step(PrPlan* plan, const float* d_r_old, float* d_r_new, float damping, c
             const uint32_t* d_bits, double* d_partial, cudaStream_t stream,
             float* const* peer_r_new = nullptr, int n_peers = 0, int self_rank = 0, float* mc_r_new = nullptr);
 const CsrView& pr_plan_view(const PrPlan* plan);
+int pr_plan_hub_columns(const PrPlan* plan);  // entries of the shared-memory x table in use (0: none)
 double* pr_plan_tmp(PrPlan* plan);
 int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,
                     float* final_residual, bool* converged, double* l1_residual, bool normalize = true, float* l2_history = nullptr, int history_capacity = 0);

@@ -145,6 +145,10 @@ int pr_step(PrPlan* p, const float* d_r_old, float* d_r_new, float damping, cons
 }
 
 const CsrView& pr_plan_view(const PrPlan* p) { return p->A; }
+int pr_plan_hub_columns(const PrPlan* p) {
+    if (!p) return 0;
+    return p->planned.seg.valid() ? p->planned.seg.n_hot : p->planned.hot.n_hot;
+}
 double* pr_plan_tmp(PrPlan* p) { return p->tmp; }
 
 // The whole loop on one device; d_ranks receives the ranks, normalised on the device with an
@@ -173,13 +177,14 @@ int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d
     const int cols = adj->num_cols;
     const size_t colsum_n = static_cast<size_t>(cols > n ? cols : n);
     const size_t words = (static_cast<size_t>(n) + 31) / 32;
-    float *d_a = nullptr, *d_b = nullptr, *d_colsum = nullptr, *d_dsum = nullptr;
+    float *d_a = nullptr, *d_b = nullptr, *d_dsum = nullptr;
+    double* d_colsum = nullptr;
     uint32_t* d_bits = nullptr;
     double* d_partial = nullptr;
     double* h_partial = nullptr;
     bool ok = cudaMalloc(&d_a, sizeof(float) * n) == cudaSuccess &&
               cudaMalloc(&d_b, sizeof(float) * n) == cudaSuccess &&
-              cudaMalloc(&d_colsum, sizeof(float) * colsum_n) == cudaSuccess &&
+              cudaMalloc(&d_colsum, sizeof(double) * colsum_n) == cudaSuccess &&
               cudaMalloc(&d_bits, sizeof(uint32_t) * words) == cudaSuccess &&
               cudaMalloc(&d_dsum, sizeof(float)) == cudaSuccess &&
               cudaMalloc(&d_partial, 3 * sizeof(double)) == cudaSuccess &&
@@ -196,7 +201,7 @@ int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d
     }
 
     // dangling nodes: columns whose stored values sum to 0 (reference :20-48, :87)
-    cudaMemsetAsync(d_colsum, 0, sizeof(float) * colsum_n, stream);
+    cudaMemsetAsync(d_colsum, 0, sizeof(double) * colsum_n, stream);
     launch_colsum(plan->A, d_colsum, stream);
     launch_dangling_bits(d_colsum, n, cols, d_bits, stream);
     // r = 1/n and its dangling mass (reference :69-72, :94-99 for iteration 0)

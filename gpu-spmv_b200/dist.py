@@ -202,7 +202,7 @@ class CudaShard:
 
     def setup_dangling(self, group=None):
         """Dangling columns = global column sums equal to 0 (src/pagerank.cu:20-48)."""
-        colsum = torch.zeros(self.n, dtype=torch.float32, device=self.dev)
+        colsum = torch.zeros(self.n, dtype=torch.float64, device=self.dev)
         rc = sp.lib.spmv_b200_pr_colsum(self.plan, sp.dptr(colsum), self._s())
         assert rc == 0
         if dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -346,3 +346,75 @@ def pagerank_sharded(shard, bounds, damping=0.85, tolerance=1e-6, max_iterations
     fin, iters, residual, conv, l1 = pagerank_loop(shard, r_a, r_b, partial, bounds, damping, tolerance,
                                                     max_iterations, group, fixed_iterations)
     return PageRankOutcome(shard.normalize(fin), iters, residual, conv, l1)
+
+
+# ------------------------------------------- native sharded PageRank (csrc/pagerank_dist.cu) ----
+# The loop above (pagerank_loop / CudaShard) is the round-1 Python orchestration, kept for the
+# backend-agnostic gloo tests.  The product path is the C++ one below: rendezvous, symmetric
+# memory, multicast binding, in-kernel flag barrier and CUDA-graph replay all live in
+# libspmv_b200.so; Python only passes pointers.
+
+EXCHANGE_AUTO, EXCHANGE_NCCL, EXCHANGE_P2P, EXCHANGE_MULTICAST = -1, 0, 1, 2
+EXCHANGE_NAMES = {0: "nccl", 1: "p2p", 2: "multicast"}
+
+
+class PrDistResult(C.Structure):  # include/spmv_b200.h: spmv_b200_pr_dist_result
+    _fields_ = [("iterations", C.c_int), ("final_residual", C.c_float), ("converged", C.c_int),
+                ("l1_residual", C.c_double), ("iterations_launched", C.c_int), ("device_seconds", C.c_double),
+                ("wall_seconds", C.c_double), ("exchange", C.c_int), ("graph_replay", C.c_int),
+                ("kernels_per_iteration", C.c_int)]
+
+
+class NativeComm:
+    """spmv_b200_comm_*: one process per GPU, abstract unix socket named after `session`."""
+
+    def __init__(self, rank, world, session, timeout_s=300):
+        self.rank, self.world = int(rank), int(world)
+        self.handle = C.c_void_p()
+        rc = sp.lib.spmv_b200_comm_create(self.rank, self.world, str(session).encode(), int(timeout_s), C.byref(self.handle))
+        if rc != 0:
+            raise RuntimeError(f"comm_create(rank {rank} of {world}, session {session}): {sp.spmv_error_string(rc)}")
+
+    def barrier(self):
+        assert sp.lib.spmv_b200_comm_barrier(self.handle) == 0
+
+    def allgather_doubles(self, value):
+        send = (C.c_double * 1)(float(value))
+        recv = (C.c_double * self.world)()
+        assert sp.lib.spmv_b200_comm_allgather(self.handle, send, recv, 8) == 0
+        return list(recv)
+
+    def close(self):
+        if self.handle:
+            sp.lib.spmv_b200_comm_destroy(self.handle)
+            self.handle = None
+
+
+class NativeShardedPageRank:
+    """spmv_b200_pr_dist_*: this rank's shard (a DeviceCSR with global column ids) of a sharded PageRank."""
+
+    def __init__(self, comm, csr, row_offset, n_global, exchange=EXCHANGE_AUTO):
+        self.comm, self.csr, self.n = comm, csr, int(n_global)
+        self.handle = C.c_void_p()
+        rc = sp.lib.spmv_b200_pr_dist_create(comm.handle, csr.ptr, int(row_offset), self.n, int(exchange), C.byref(self.handle))
+        if rc != 0:
+            raise RuntimeError(f"pr_dist_create: {sp.spmv_error_string(rc)}")
+        self.exchange = sp.lib.spmv_b200_pr_dist_exchange(self.handle)
+        self.hub_columns = sp.lib.spmv_b200_pr_dist_hub_columns(self.handle)
+
+    def run(self, damping=0.85, tolerance=1e-6, max_iterations=100, fixed_iterations=0):
+        cfg = sp.make_pagerank_config(damping, tolerance, max_iterations)
+        res = PrDistResult()
+        rc = sp.lib.spmv_b200_pr_dist_run(self.handle, C.byref(cfg), int(fixed_iterations), C.byref(res))
+        if rc != 0:
+            raise RuntimeError(f"pr_dist_run: {sp.spmv_error_string(rc)}")
+        return res
+
+    def ranks(self, device):
+        ptr = sp.lib.spmv_b200_pr_dist_ranks(self.handle)
+        return _tensor_from_ptr(ptr, self.n, device)
+
+    def close(self):
+        if self.handle:
+            sp.lib.spmv_b200_pr_dist_destroy(self.handle)
+            self.handle = None

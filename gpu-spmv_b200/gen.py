@@ -150,6 +150,78 @@ def rmat_pagerank_csr(scale, edge_factor, seed, device):
     return n, row_ptrs.to(torch.int32), cols.to(torch.int32), vals
 
 
+def relabel(v, scale):
+    """Bijective pseudo-random relabelling of vertex ids in [0, 2^scale) (xorshift, odd multiply,
+    xorshift), the role of Graph500's vertex permutation: it removes R-MAT's id/degree correlation."""
+    mask = (1 << scale) - 1
+    v = v ^ (v >> (scale // 2))
+    v = (v * 0x9E3779B1 + 0x7F4A7C15) & mask
+    return v ^ (v >> (scale // 2 + 1))
+
+
+def partition_bounds(row_ptrs, parts, row_weight=0):
+    """Contiguous row split balancing work(row) = nnz(row) + row_weight: bounds[p] = first row whose
+    prefix work row_ptrs[i] + i * row_weight reaches p * total / parts (same rule as
+    spmv_b200_partition_rows_weighted).  row_ptrs: int64 tensor [rows + 1] on any device."""
+    rows = row_ptrs.numel() - 1
+    prefix = row_ptrs[:rows].to(torch.int64) + torch.arange(rows, dtype=torch.int64, device=row_ptrs.device) * row_weight
+    total = int(row_ptrs[-1].item()) + rows * row_weight
+    targets = torch.tensor([(total * p) // parts for p in range(1, parts)], dtype=torch.int64, device=row_ptrs.device)
+    inner = torch.searchsorted(prefix, targets, right=False).tolist() if parts > 1 else []
+    bounds = [0] + [int(b) for b in inner] + [rows]
+    for p in range(1, parts + 1):
+        bounds[p] = max(bounds[p], bounds[p - 1])
+    return bounds
+
+
+def rmat_pagerank_shard(scale, edge_factor, seed, rank, world, device, chunk=1 << 24, row_weight=1, relabelled=False):
+    """Rank `rank`'s row shard of rmat_pagerank_csr(scale, edge_factor, seed) WITHOUT materialising the
+    whole graph: pass 1 counts in/out degrees of every edge (bincount), pass 2 keeps the edges whose
+    destination falls in this rank's row range (work(row) = nnz + row_weight balanced) and sorts only
+    those.  Returns (n, bounds, row_ptrs i32 rebased to 0, col_indices i32 global, values f32, n_edges);
+    concatenating the shards of all ranks gives exactly rmat_pagerank_csr's arrays."""
+    n = 1 << scale
+    n_edges = edge_factor << scale
+    indeg = torch.zeros(n, dtype=torch.int64, device=device)
+    outdeg = torch.zeros(n, dtype=torch.int64, device=device)
+    ta = int(RMAT_A * 4294967296.0)
+    tb = int((RMAT_A + RMAT_B) * 4294967296.0)
+    tc = int((RMAT_A + RMAT_B + RMAT_C) * 4294967296.0)
+
+    def edges(lo, hi):
+        e = torch.arange(lo, hi, dtype=torch.int64, device=device)
+        s = torch.zeros_like(e)
+        d = torch.zeros_like(e)
+        for level in range(scale):
+            u = hash32(seed, e, stream=16 + level)
+            s = (s << 1) | (u >= tb).to(torch.int64)
+            d = (d << 1) | (((u >= ta) & (u < tb)) | (u >= tc)).to(torch.int64)
+        if relabelled:
+            s, d = relabel(s, scale), relabel(d, scale)
+        return s, d
+
+    for lo in range(0, n_edges, chunk):
+        s, d = edges(lo, min(lo + chunk, n_edges))
+        indeg += torch.bincount(d, minlength=n)
+        outdeg += torch.bincount(s, minlength=n)
+    row_ptrs = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    row_ptrs[1:] = torch.cumsum(indeg, dim=0)
+    bounds = partition_bounds(row_ptrs, world, row_weight)
+    r_lo, r_hi = bounds[rank], bounds[rank + 1]
+    keys = []
+    for lo in range(0, n_edges, chunk):
+        s, d = edges(lo, min(lo + chunk, n_edges))
+        m = (d >= r_lo) & (d < r_hi)
+        keys.append(((d[m] << 32) | s[m]))
+    key = torch.cat(keys) if keys else torch.zeros(0, dtype=torch.int64, device=device)
+    del keys
+    key, _ = torch.sort(key)
+    cols = (key & 0xFFFFFFFF)
+    vals = torch.ones((), dtype=torch.float32, device=device) / outdeg.to(torch.float32)[cols]
+    rp_local = (row_ptrs[r_lo:r_hi + 1] - row_ptrs[r_lo]).to(torch.int32)
+    return n, bounds, rp_local, cols.to(torch.int32), vals, n_edges
+
+
 def random_csr(rows, cols, avg_nnz, seed, device, skew=0.0):
     """General random test matrix: row lengths around avg_nnz (optionally a
     heavy tail when skew > 0), columns from the hash, values U[-1, 1).

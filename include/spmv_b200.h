@@ -263,6 +263,27 @@ SPMV_B200_API int spmv_b200_spmv_csr_async(const spmv_b200_csr* A, const float* 
 SPMV_B200_API int spmv_b200_spmv_ell_async(const spmv_b200_ell* A, const float* d_x, float* d_y,
                                            void* stream);
 
+/* ---- host-buffer SpMV, pipelined ------------------------------------------
+ * y_host = A x_host for an ELL matrix resident on the device while x and y live in HOST memory:
+ * what a caller of the reference writes as cudaMemcpy(x) + spmv_ell + cudaMemcpy(y)
+ * (reference README.md:98-118, src/benchmark.cu:36-38,95-102), with the upload of x, the product
+ * and the download of y pipelined over row chunks on three streams.  The plan measures, once,
+ * which x entries every row chunk reads (its column range), so a banded matrix overlaps the PCIe
+ * up- and down-link almost completely; any other matrix degenerates to upload, then compute
+ * overlapped with the download.  y is bit-identical to spmv_ell.  The matrix's device arrays are
+ * borrowed and must outlive the plan.  chunks <= 0: 8.  x_host / y_host should be page-locked. */
+typedef struct spmv_b200_ell_host_plan spmv_b200_ell_host_plan;
+SPMV_B200_API int spmv_b200_ell_host_plan_create(const spmv_b200_ell* A, int chunks,
+                                                 spmv_b200_ell_host_plan** out);
+SPMV_B200_API void spmv_b200_ell_host_plan_destroy(spmv_b200_ell_host_plan* plan);
+/* blocking: returns when y_host is complete */
+SPMV_B200_API int spmv_b200_spmv_ell_host(spmv_b200_ell_host_plan* plan, const float* x_host,
+                                          float* y_host);
+/* chunks in use; whether the row-range kernel applies; the largest number of x chunks beyond its
+ * own index any row chunk has to wait for (0-1 for a banded matrix, chunks - 1 in the worst case) */
+SPMV_B200_API int spmv_b200_ell_host_plan_info(const spmv_b200_ell_host_plan* plan, int* chunks,
+                                               int* ranged, int* max_lookahead);
+
 /* device-side ELL assembly from the DEVICE arrays of csr (ell_from_csr
  * semantics, src/ell_matrix.cpp:111-159); fills ell's device arrays only
  * (allocates them, sets owns_device_memory) and dims. */
@@ -357,9 +378,15 @@ SPMV_B200_API int spmv_b200_csr_plan_info(const spmv_b200_csr_plan* plan, int* h
  * different (fixed) order and agree within the fp32 SpMV tolerance. */
 SPMV_B200_API int spmv_b200_spmv_csr_planned(const spmv_b200_csr_plan* plan, const float* d_x,
                                              float* d_y, void* stream);
-/* spmv_csr(MERGE_PATH) attaches such a plan by itself to device arrays uploaded by csr_to_gpu
- * (second call onwards; SPMV_B200_HOT=0 disables).  After overwriting d_col_indices of such an
- * upload IN PLACE, drop the stale plan with this call (csr_to_gpu / csr_free_gpu do it). */
+/* OPT-IN automatic plans (off by default; also SPMV_B200_AUTO_PLAN=1): when enabled,
+ * spmv_csr(MERGE_PATH) attaches such a plan by itself to device arrays uploaded by csr_to_gpu, from
+ * the second call on.  Off by default because the reference's d_col_indices / d_row_ptrs fields are
+ * public and may legally be rewritten in place (reference include/spmv/csr_matrix.h:11-28): a plan
+ * keeps a private re-encoding of both, so results would silently follow the OLD pattern.  A caller
+ * that enables it must call spmv_b200_csr_forget_plan after such an edit (csr_to_gpu / csr_free_gpu /
+ * csr_destroy drop the plan themselves).  Costs 4 B of device memory per non-zero. */
+SPMV_B200_API void spmv_b200_set_auto_plan(int enabled);
+SPMV_B200_API int spmv_b200_auto_plan_enabled(void);
 SPMV_B200_API void spmv_b200_csr_forget_plan(const spmv_b200_csr* A);
 /* the automatic plan currently attached to A's device arrays (hot_columns == 0: none) */
 SPMV_B200_API int spmv_b200_csr_auto_plan_info(const spmv_b200_csr* A, int* hot_columns,
@@ -381,10 +408,11 @@ SPMV_B200_API void spmv_b200_pr_plan_destroy(spmv_b200_pr_plan* plan);
 SPMV_B200_API int spmv_b200_pr_plan_set_hot(spmv_b200_pr_plan* plan, int max_hot_columns, int force,
                                             void* stream);
 
-/* d_colsum[c] += sum of this shard's values in column c (fp32 atomics) */
-SPMV_B200_API int spmv_b200_pr_colsum(const spmv_b200_pr_plan* plan, float* d_colsum, void* stream);
-/* d_bits[c/32] bit c%32 = (d_colsum[c] == 0.0f)  (dangling columns) */
-SPMV_B200_API int spmv_b200_pr_dangling_bits(const float* d_colsum, int n, uint32_t* d_bits,
+/* d_colsum[c] += sum of this shard's values in column c; f64 accumulators: a sum that is never
+ * rounded does not depend on the order of the atomics, so the dangling set is deterministic */
+SPMV_B200_API int spmv_b200_pr_colsum(const spmv_b200_pr_plan* plan, double* d_colsum, void* stream);
+/* d_bits[c/32] bit c%32 = ((float)d_colsum[c] == 0.0f)  (dangling columns) */
+SPMV_B200_API int spmv_b200_pr_dangling_bits(const double* d_colsum, int n, uint32_t* d_bits,
                                              void* stream);
 /* d_r[i] = 1.0f / n for the whole vector; d_dsum[0] = mass on dangling nodes */
 SPMV_B200_API int spmv_b200_pr_init(int n, const uint32_t* d_bits, float* d_r, float* d_dsum,
@@ -457,6 +485,71 @@ SPMV_B200_API int spmv_b200_pagerank_device_history(const spmv_b200_csr* adj,
                                                     float* d_ranks, int* iterations,
                                                     float* final_residual, bool* converged,
                                                     float* l2_history, int history_capacity);
+
+/* ---- multi-GPU PageRank, host side in C++ ---------------------------------
+ * The reference has no multi-GPU code.  This is the multi-GPU member of its signature family
+ * pagerank(adj, config) -> ranks (reference include/spmv/pagerank.h:29-32, src/pagerank.cu:50-153):
+ * contiguous row shards over the <= 8 GPUs of one NVSwitch box, every rank holding the full rank
+ * vector.  Per iteration and rank: a 1-warp gate (waits for the peers' flags, folds the ranks'
+ * partial sums in rank order), the fused step kernel (which also stores every finished rank value
+ * into every GPU's vector: one multimem.st through the NVSwitch multicast mapping, or unicast peer
+ * stores), a 1-warp publish (partial sums + flag to every peer) -- replayed from a CUDA graph, no
+ * collective-library call and no host round trip between iterations.  The literal "NCCL all-gather
+ * + all-reduce" transport is kept as SPMV_B200_EXCHANGE_NCCL (libnccl is dlopen'ed on first use).
+ * All transports give bit-identical vectors. */
+enum {
+    SPMV_B200_EXCHANGE_AUTO = -1,      /* multicast if the box has NVLS, else peer stores, else NCCL */
+    SPMV_B200_EXCHANGE_NCCL = 0,
+    SPMV_B200_EXCHANGE_P2P = 1,
+    SPMV_B200_EXCHANGE_MULTICAST = 2
+};
+typedef struct {
+    int iterations;             /* as PageRankResult (reference include/spmv/pagerank.h:18-26) */
+    float final_residual;
+    int converged;
+    double l1_residual;
+    int iterations_launched;    /* includes the speculative iteration after convergence */
+    double device_seconds;      /* CUDA events around the loop (max over ranks for pagerank_multi) */
+    double wall_seconds;
+    int exchange;               /* transport actually used (SPMV_B200_EXCHANGE_*) */
+    int graph_replay;           /* 1: the iteration was replayed from a CUDA graph */
+    int kernels_per_iteration;
+} spmv_b200_pr_dist_result;
+
+/* One process, n_gpus devices (devices == NULL: 0 .. n_gpus-1): adj is a HOST CSR (host arrays);
+ * shards balance work(row) = nnz + row_weight; ranks_out is a host array of num_rows floats
+ * (normalised, as pagerank()).  fixed_iterations > 0 runs exactly that many (no stop rule). */
+SPMV_B200_API int spmv_b200_pagerank_multi(const spmv_b200_csr* adj, const spmv_b200_pagerank_config* config,
+                                           int n_gpus, const int* devices, int exchange, int row_weight,
+                                           int fixed_iterations, float* ranks_out,
+                                           spmv_b200_pr_dist_result* out);
+
+/* One process PER GPU (torchrun, mpirun, any launcher): a communicator for the set-up traffic
+ * (shard bounds, NCCL id, descriptors of the symmetric allocations) over an abstract unix-domain
+ * socket named after `session` (the same string on every rank, unique per job; one box only). */
+typedef struct spmv_b200_comm spmv_b200_comm;
+SPMV_B200_API int spmv_b200_comm_create(int rank, int world, const char* session, int timeout_s,
+                                        spmv_b200_comm** out);
+SPMV_B200_API void spmv_b200_comm_destroy(spmv_b200_comm* comm);
+SPMV_B200_API int spmv_b200_comm_barrier(spmv_b200_comm* comm);
+SPMV_B200_API int spmv_b200_comm_allgather(spmv_b200_comm* comm, const void* send, void* recv, size_t bytes);
+/* every rank passes one open file descriptor and receives world new ones (SCM_RIGHTS) */
+SPMV_B200_API int spmv_b200_comm_allgather_fds(spmv_b200_comm* comm, int my_fd, int* fds_out);
+
+/* Sharded PageRank object: collective calls (every rank, same order).  shard = this rank's rows
+ * [row_offset, row_offset + shard->num_rows) with global column ids, device arrays present
+ * (borrowed).  The current device of the calling thread is the rank's GPU. */
+typedef struct spmv_b200_pr_dist spmv_b200_pr_dist;
+SPMV_B200_API int spmv_b200_pr_dist_create(spmv_b200_comm* comm, const spmv_b200_csr* shard, int row_offset,
+                                           int n_global, int exchange, spmv_b200_pr_dist** out);
+SPMV_B200_API int spmv_b200_pr_dist_run(spmv_b200_pr_dist* d, const spmv_b200_pagerank_config* config,
+                                        int fixed_iterations, spmv_b200_pr_dist_result* out);
+/* device pointer to the full, normalised rank vector of the last run (identical on every rank) */
+SPMV_B200_API const float* spmv_b200_pr_dist_ranks(const spmv_b200_pr_dist* d);
+SPMV_B200_API int spmv_b200_pr_dist_exchange(const spmv_b200_pr_dist* d);
+SPMV_B200_API int spmv_b200_pr_dist_hub_columns(const spmv_b200_pr_dist* d);
+SPMV_B200_API void spmv_b200_pr_dist_destroy(spmv_b200_pr_dist* d);
+SPMV_B200_API int spmv_b200_nccl_available(void);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -205,15 +205,21 @@ def test_pagerank_with_and_without_a_plan(sp, orc, cuda):
 
 
 def test_spmv_csr_attaches_a_plan_to_csr_to_gpu_uploads(sp, orc, cuda):
-    """Drop-in path: spmv_csr(MERGE_PATH) on arrays uploaded by csr_to_gpu builds the plan on the
-    second call (large scale-free matrix), later calls run the hub-table kernel with identical
-    results; csr_forget_plan / csr_free_gpu drop it."""
+    """Drop-in path with automatic plans switched ON (they are opt-in: off by default, a drop-in must
+    not cache the sparsity pattern behind the caller's back): spmv_csr(MERGE_PATH) on arrays uploaded
+    by csr_to_gpu builds the plan on the second call (large scale-free matrix), later calls run the
+    hub-table kernel with identical results; csr_forget_plan / csr_free_gpu drop it."""
     from gpu_helpers import GpuCSR, run_csr
     gen = gen_mod()
     n, rp, ci, va = gen.rmat_pagerank_csr(19, 16, 21, "cpu")
     x = gen.vector_pm1(n, 5, "cpu").numpy()
     A = GpuCSR(sp, n, n, rp.numpy(), ci.numpy(), va.numpy())
     y64, scale = orc.spmv_csr_f64(n, A.rp, A.ci, A.va, x)
+    assert sp.lib.spmv_b200_auto_plan_enabled() == 0  # default: off
+    for _ in range(3):
+        y0, _ = run_csr(sp, A.mat, x, MERGE, cuda, n)
+        assert sp.csr_auto_plan_info(A.mat) == (0, 0)
+    sp.lib.spmv_b200_set_auto_plan(1)
     y1, _ = run_csr(sp, A.mat, x, MERGE, cuda, n)
     assert sp.csr_auto_plan_info(A.mat) == (0, 0)
     y2, _ = run_csr(sp, A.mat, x, MERGE, cuda, n)
@@ -227,7 +233,8 @@ def test_spmv_csr_attaches_a_plan_to_csr_to_gpu_uploads(sp, orc, cuda):
     sp.csr_forget_plan(A.mat)
     assert sp.csr_auto_plan_info(A.mat) == (0, 0)
     y4, _ = run_csr(sp, A.mat, x, MERGE, cuda, n)
-    assert np.array_equal(bits(y1), bits(y4))
+    assert np.array_equal(bits(y1), bits(y4)) and np.array_equal(bits(y0), bits(y1))
+    sp.lib.spmv_b200_set_auto_plan(0)
     A.close()
 
 

@@ -156,7 +156,7 @@ def test_device_resident_api_and_shards_on_one_gpu(sp, orc, cuda):
     for s in shards:
         s.setup_dangling()
     # every shard contributes its own column sums; emulate the all-reduce by summing bits' sources
-    colsum = torch.zeros(n, device=cuda)
+    colsum = torch.zeros(n, dtype=torch.float64, device=cuda)
     for s in shards:
         assert sp.lib.spmv_b200_pr_colsum(s.plan, sp.dptr(colsum), None) == 0
     for s in shards:

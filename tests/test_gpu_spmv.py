@@ -5,6 +5,8 @@ by tests/test_oracle_pinned.py) and its f64-accumulating variant for the
 north_star tolerance |y - y_ref| <= 1e-5 * sum_j |a_ij x_j| per row.
 SCALAR_CSR and ELL keep the reference CPU path's operation order, so they are
 checked BIT-EXACT against it."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -369,3 +371,77 @@ def test_every_kernel_variant_forced(cuda, env):
            "-k", "random_shapes or outlier_rows or unaligned or laplacian_medium or golden"]
     p = subprocess.run(cmd, env={**os.environ, **env}, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert p.returncode == 0, p.stdout[-3000:]
+
+
+def test_products_in_place_kernel_is_bit_identical(sp, orc, cuda):
+    """csr_prod_kernel (SCALAR / one-lane VECTOR on short-row matrices: TMA-staged window, products in
+    place in stream order, then one thread per row front to back) against spmv_cpu_csr, bit for bit,
+    on shapes that exercise the unstaged tail (nnz % 4 != 0), empty rows, rows == 1, a last window
+    whose row_ptrs cannot be bulk-copied, and unaligned window starts."""
+    gen = gen_mod()
+    cases = [(1, 7, 3), (5, 5, 2), (257, 300, 3), (1000, 999, 5), (4099, 4099, 4), (70001, 70001, 6), (262144, 262144, 5)]
+    for rows, cols, avg in cases:
+        rp, ci, va = gen.random_csr(rows, cols, avg, seed=rows + avg, device="cpu")
+        x = gen.vector_pm1(cols, 3, "cpu").numpy()
+        A = GpuCSR(sp, rows, cols, rp.numpy(), ci.numpy(), va.numpy())
+        y_cpu = orc.spmv_csr(rows, A.rp, A.ci, A.va, x)
+        for kernel in (sp.SCALAR_CSR, sp.VECTOR_CSR):
+            if kernel == sp.VECTOR_CSR and avg >= 6:
+                continue  # several lanes per row: tolerance, covered elsewhere
+            y, _ = run_csr(sp, A.mat, x, kernel, cuda, rows)
+            assert np.array_equal(bits(y), bits(y_cpu)), (rows, cols, avg, kernel)
+        A.close()
+    # the Laplacian stencil (config 2 at 1024^2): the shape the kernel exists for
+    grid = 1024
+    n = grid * grid
+    rp, ci, va = gen.laplacian_2d_csr(grid, "cpu")
+    x = gen.vector_pm1(n, 42, "cpu").numpy()
+    A = GpuCSR(sp, n, n, rp.numpy(), ci.numpy(), va.numpy())
+    y, _ = run_csr(sp, A.mat, x, sp.SCALAR_CSR, cuda, n)
+    assert np.array_equal(bits(y), bits(orc.spmv_csr(n, A.rp, A.ci, A.va, x)))
+    A.close()
+
+
+def test_pipelined_host_buffer_ell(sp, orc, cuda):
+    """spmv_b200_spmv_ell_host: x and y in (pinned) HOST memory, upload / product / download pipelined
+    over row chunks by the measured column range of every chunk.  Bit-identical to spmv_cpu_ell for a
+    banded matrix (chunks run ahead of the upload), for a matrix whose rows read all of x (no run-ahead),
+    for a shape the row-range kernel does not cover (rows % 4 != 0: single launch), and re-usable."""
+    gen = gen_mod()
+
+    def check(rows, cols, rp, ci, va, chunks, expect_ranged, expect_lookahead_small):
+        x = gen.vector_pm1(cols, 11, "cpu").numpy()
+        A = GpuCSR(sp, rows, cols, rp, ci, va)
+        E = sp.ell_create(0, 0, 0)
+        assert sp.ell_from_csr(E, A.mat) == 0 and sp.ell_to_gpu(E) == 0
+        w = E.contents.max_nnz_per_row
+        ec, ev = sp.ell_arrays(E)
+        y_cpu = orc.spmv_ell(rows, w, ec, ev, x)
+        plan = C.c_void_p()
+        assert sp.lib.spmv_b200_ell_host_plan_create(E, chunks, C.byref(plan)) == 0
+        n_chunks, ranged, look = C.c_int(), C.c_int(), C.c_int()
+        assert sp.lib.spmv_b200_ell_host_plan_info(plan, C.byref(n_chunks), C.byref(ranged), C.byref(look)) == 0
+        assert bool(ranged.value) == expect_ranged
+        if expect_lookahead_small:
+            assert look.value <= 1
+        xh = torch.as_tensor(x).pin_memory()
+        yh = torch.full((rows,), float("nan")).pin_memory()
+        for rep in range(3):
+            yh.fill_(float("nan"))
+            assert sp.lib.spmv_b200_spmv_ell_host(plan, xh.data_ptr(), yh.data_ptr()) == 0
+            assert np.array_equal(bits(yh.numpy()), bits(y_cpu)), (rows, cols, chunks, rep)
+        # pageable buffers work too
+        yp = np.full(rows, np.nan, np.float32)
+        assert sp.lib.spmv_b200_spmv_ell_host(plan, x.ctypes.data, yp.ctypes.data) == 0
+        assert np.array_equal(bits(yp), bits(y_cpu))
+        sp.lib.spmv_b200_ell_host_plan_destroy(plan)
+        sp.ell_destroy(E)
+        A.close()
+
+    grid = 512
+    rp, ci, va = gen.laplacian_2d_csr(grid, "cpu")
+    check(grid * grid, grid * grid, rp.numpy(), ci.numpy(), va.numpy(), 16, True, True)
+    rp, ci, va = gen.random_csr(40000, 40000, 3, seed=5, device="cpu")
+    check(40000, 40000, rp.numpy(), ci.numpy(), va.numpy(), 8, int(np.diff(rp.numpy()).max()) <= 8, False)
+    rp, ci, va = gen.random_csr(30001, 50000, 2, seed=6, device="cpu")
+    check(30001, 50000, rp.numpy(), ci.numpy(), va.numpy(), 4, False, False)
