@@ -9,17 +9,25 @@ ELL SpMV over BASELINE config 2 (5-point Laplacian on a 4096^2 grid, 16.7 M
 rows, 83.9 M non-zeros, 805 MB of matrix -- larger than L2, so no flush is
 needed between iterations).  `value` is whole-job effective HBM GB/s =
 algorithmic bytes (reference src/bandwidth.cpp:66-75) x steps / device time,
-inputs resident in HBM.  `e2e` is the same metric through the blocking
-reference-facing C-ABI call with HOST x / y buffers (H2D of x and D2H of y in
-the timed region).  `extra` carries the other BASELINE configurations
-(CSR kernels on config 2, config 3, config 4 R-MAT SpMV -- plain merge-path and
-through a hub-column plan --, PageRank iter/s).
+inputs resident in HBM.  `e2e` is the same metric through the reference-facing
+C-ABI call that takes HOST x / y buffers (spmv_b200_spmv_ell_host: H2D of x,
+kernel and D2H of y pipelined over row chunks, all inside the timed region).
 
-N > 1 (one rank per GPU, NCCL): weak scaling for the headline -- every rank
-owns a 16.7 M-row band (row shard) of a 4096 x (4096 N) Laplacian with the
-vector replicated, no data-path collective; `extra.pagerank` is the
-row-sharded PageRank with the rank-vector all-gather and the 3-double
-all-reduce over NCCL (strong scaling: one R-MAT graph split over N ranks).
+BASELINE.json's metric has a second half -- PageRank iterations/s at 1/2/4/8
+GPUs on R-MAT 26 -- and a sharded SpMV case (config 4, R-MAT 24 merge-path).
+Both are measured in the same run and reported as TOP-LEVEL scalars of the
+line (`pagerank_iters_per_s`, `pagerank_ms_per_iter`, `pagerank_exchange`,
+`pagerank_1gpu_iters_per_s`, `pagerank_speedup_vs_1gpu`, `rmat24_merge_frac`,
+`config2_csr_frac`, ...), with the details under `extra`.  The sharded
+PageRank runs through the native C++ path (spmv_b200_pr_dist_*: strong
+scaling, one graph split over the N ranks); before it is timed, `parity`
+checks it against the CPU oracle (scale-20 graph, every transport, 10 fixed
+iterations, L1 <= 1e-6, transports bit-identical) and, at full size, that every
+rank holds the bit-identical vector with sum 1 -- a mismatch makes the run fail.
+
+N > 1 (one rank per GPU): weak scaling for the headline -- every rank owns a
+16.7 M-row band (row shard) of a 4096 x (4096 N) Laplacian with the vector
+replicated, no data-path collective.
 
 --impl reference times the reference's own CPU implementation of the step
 (spmv_cpu_ell from oracle/_ref, the unmodified reference sources; the oracle
@@ -97,13 +105,30 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- reference arm
 
+WORKLOAD = ("config2: 5-point Laplacian 4096x4096 grid per GPU (16.7M rows, 83.9M nnz), ELL width 5, spmv_ell; "
+            "x = hash U[-1,1)")
+
+
+def headline_config(rows, nnz, bytes_per_step, world):
+    """`config` of the JSON line -- the same keys and strings in both arms (same_config at N = 1)."""
+    return {"workload": WORKLOAD, "rows": rows, "nnz": nnz, "bytes_per_step": bytes_per_step,
+            "l2": "inputs (805 MB per GPU) larger than L2 / LLC, no flush",
+            "parallelism": f"row shards x{world}, x replicated"}
+
+
+def standalone_gen():
+    """gpu-spmv_b200/gen.py loaded as a plain module (pure torch): the reference arm must not load the
+    product package, whose import pulls in libspmv_b200.so."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("spmv_bench_gen", os.path.join(ROOT, "gpu-spmv_b200", "gen.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def build_config2_host(rows_lo, rows_hi, grid_y):
-    """Config-2 band as host ELL arrays (ell_from_csr semantics) + x, generated on the CPU."""
-    import numpy as np
-    import torch
-    from _load_pkg import load_pkg
-    load_pkg()
-    import gpu_spmv_b200.gen as gen
+    """Config-2 band as host CSR arrays + x, generated on the CPU (no product code involved)."""
+    gen = standalone_gen()
     rp, ci, va = gen.laplacian_band_csr(GRID, rows_lo, rows_hi, grid_y, "cpu")
     x = gen.vector_pm1(GRID * grid_y, SEED_X, "cpu").numpy()
     return rp.numpy(), ci.numpy(), va.numpy(), x
@@ -111,7 +136,7 @@ def build_config2_host(rows_lo, rows_hi, grid_y):
 
 def cpu_reference_time(rp, ci, va, x, rows, cols, reps):
     """Seconds per spmv_cpu_ell pass through the unmodified reference (oracle/_ref), else the
-    oracle port.  Returns (seconds, kind, threads)."""
+    oracle port.  Returns (seconds, kind, threads, y of the last pass)."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_binding import Oracle, Ref
@@ -126,14 +151,14 @@ def cpu_reference_time(rp, ci, va, x, rows, cols, reps):
         sec = ref.L.ref_time_spmv_cpu_ell(he, x.ctypes.data_as(fp), y.ctypes.data_as(fp), reps)
         ref.L.ref_ell_destroy(he)
         ref.L.ref_csr_destroy(h)
-        return sec, "reference", 1
+        return sec, "reference", 1, y
     orc = Oracle()
     w, ec, ev = orc.ell_from_csr(rows, rp, ci, va)
     orc.spmv_ell(rows, w, ec, ev, x)
     t0 = time.perf_counter()
     for _ in range(reps):
-        orc.spmv_ell(rows, w, ec, ev, x)
-    return (time.perf_counter() - t0) / reps, "port", 1
+        y = orc.spmv_ell(rows, w, ec, ev, x)
+    return (time.perf_counter() - t0) / reps, "port", 1, y
 
 
 def run_reference_arm(args):
@@ -144,22 +169,21 @@ def run_reference_arm(args):
     # bounded sample: a probe band sizes the per-step sample so that steps + warm-up stay near 2 minutes
     probe_rows = 1 << 20
     rp, ci, va, x = build_config2_host(0, probe_rows, GRID)
-    probe_sec, _, _ = cpu_reference_time(rp, ci, va, x, probe_rows, n_full, 2)
+    probe_sec, _, _, _ = cpu_reference_time(rp, ci, va, x, probe_rows, n_full, 2)
     budget_rows = int(120.0 / max(args.steps + args.warmup, 1) / (probe_sec / probe_rows))
     n = max(probe_rows, min(n_full, budget_rows // GRID * GRID))
     rp, ci, va, x = build_config2_host(0, n, GRID)
     bytes_step = 8 * n * 5 + 4 * (n_full if n == n_full else n + GRID) + 4 * n
     for _ in range(max(args.warmup, 1) - 1):
         cpu_reference_time(rp, ci, va, x, n, n_full, 1)
-    sec, kind, threads = cpu_reference_time(rp, ci, va, x, n, n_full, args.steps)
+    sec, kind, threads, _ = cpu_reference_time(rp, ci, va, x, n, n_full, args.steps)
     gbs = bytes_step / sec / 1e9
     sample = ("the full config-2 matrix" if n == n_full else f"the first {n} rows (a band) of the config-2 matrix")
     line = {
         "impl": "reference", "metric": "spmv_effective_hbm_gbs", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: 5-point Laplacian 4096x4096 grid, ELL width 5, spmv_cpu_ell on the host",
-                   "rows": n, "nnz": 5 * n - 4 * GRID, "bytes_per_step": bytes_step},
+        "config": headline_config(n, 5 * n - 4 * GRID if n == n_full else 5 * n - 2 * (n // GRID) - GRID, bytes_step, 1),
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": kind,
                          "sample": f"{sample}, {args.steps} passes of spmv_cpu_ell per run, one pass per step "
                                    "(single-threaded: the reference has no threading)"},
@@ -204,61 +228,30 @@ def bench_kernel(torch, sp, stream, launch, bytes_per_launch, steps, warmup, dis
     return {"ms_per_step": per, "gbs": world * bytes_per_launch / (per * 1e-3) / 1e9}
 
 
-def relabel(v, scale):
-    """Bijective pseudo-random relabelling of vertex ids in [0, 2^scale) (xorshift, odd multiply,
-    xorshift), the role of Graph500's vertex permutation: it removes R-MAT's id/degree correlation."""
-    mask = (1 << scale) - 1
-    v = v ^ (v >> (scale // 2))
-    v = (v * 0x9E3779B1 + 0x7F4A7C15) & mask
-    return v ^ (v >> (scale // 2 + 1))
+def ncu_traffic_for(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_name` from the committed
+    `ncu --set full` raw page (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from the
+    capture; keyed by kernel name and by the hash of the kernel's source file, so a stale capture
+    reads as null instead of a wrong number)."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            table = json.load(f)
+        entry = table[kernel_name]
+        with open(os.path.join(ROOT, entry["source"]), "rb") as f:
+            digest = hashlib.sha256(f.read()).hexdigest()[:16]
+        if digest != entry["source_sha256_16"]:
+            return None, f"stale: {entry['source']} changed since {entry['capture']}"
+        return float(entry["dram_bytes_per_launch"]), entry["capture"]
+    except Exception as exc:  # no table, no entry: unknown
+        return None, f"unavailable ({type(exc).__name__})"
 
 
-def build_rmat_shard(torch, gen, scale, edge_factor, seed, rank, world, device, chunk=1 << 24, row_weight=1,
-                     relabelled=False):
-    """This rank's row shard of the column-normalised R-MAT matrix without materialising the
-    whole graph: pass 1 counts in/out degrees of every edge (bincount), pass 2 keeps the edges
-    whose destination falls in this rank's nnz-balanced row range and sorts only those."""
-    n = 1 << scale
-    n_edges = edge_factor << scale
-    indeg = torch.zeros(n, dtype=torch.int64, device=device)
-    outdeg = torch.zeros(n, dtype=torch.int64, device=device)
-    ta = int(gen.RMAT_A * 4294967296.0)
-    tb = int((gen.RMAT_A + gen.RMAT_B) * 4294967296.0)
-    tc = int((gen.RMAT_A + gen.RMAT_B + gen.RMAT_C) * 4294967296.0)
-
-    def edges(lo, hi):
-        e = torch.arange(lo, hi, dtype=torch.int64, device=device)
-        s = torch.zeros_like(e)
-        d = torch.zeros_like(e)
-        for level in range(scale):
-            u = gen.hash32(seed, e, stream=16 + level)
-            s = (s << 1) | (u >= tb).to(torch.int64)
-            d = (d << 1) | (((u >= ta) & (u < tb)) | (u >= tc)).to(torch.int64)
-        if relabelled:
-            s, d = relabel(s, scale), relabel(d, scale)
-        return s, d
-
-    for lo in range(0, n_edges, chunk):
-        s, d = edges(lo, min(lo + chunk, n_edges))
-        indeg += torch.bincount(d, minlength=n)
-        outdeg += torch.bincount(s, minlength=n)
-    row_ptrs = torch.zeros(n + 1, dtype=torch.int64, device=device)
-    row_ptrs[1:] = torch.cumsum(indeg, dim=0)
-    import gpu_spmv_b200.dist as D
-    bounds = D.partition_rows(row_ptrs, world, row_weight=row_weight)  # work(row) = nnz + row_weight
-    r_lo, r_hi = bounds[rank], bounds[rank + 1]
-    keys = []
-    for lo in range(0, n_edges, chunk):
-        s, d = edges(lo, min(lo + chunk, n_edges))
-        m = (d >= r_lo) & (d < r_hi)
-        keys.append(((d[m] << 32) | s[m]))
-    key = torch.cat(keys) if keys else torch.zeros(0, dtype=torch.int64, device=device)
-    del keys
-    key, _ = torch.sort(key)
-    cols = (key & 0xFFFFFFFF)
-    vals = torch.ones((), dtype=torch.float32, device=device) / outdeg.to(torch.float32)[cols]
-    rp_local = (row_ptrs[r_lo:r_hi + 1] - row_ptrs[r_lo]).to(torch.int32)
-    return n, bounds, rp_local, cols.to(torch.int32), vals, n_edges
+def vector_checksum(torch, v):
+    """Two 64-bit integer checksums of the bit pattern of a float32 device vector (order-sensitive)."""
+    bits = v.view(torch.int32).to(torch.int64)
+    idx = torch.arange(bits.numel(), dtype=torch.int64, device=v.device) % 1000003 + 1
+    return int(bits.sum().item()), int((bits * idx).sum().item())
 
 
 def run_product_arm(args):
@@ -286,10 +279,31 @@ def run_product_arm(args):
     stream = torch.cuda.Stream()
     s_ptr = stream.cuda_stream
     extra = {}
+    scalars = {}
+    parity = {}
+    session = f"bench-{os.environ.get('MASTER_PORT', '0')}-{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}-{os.getppid() if dist_on else os.getpid()}"
+    comm = D.NativeComm(rank, world, session) if dist_on else None
 
     def log(msg):
         if rank == 0:
             print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+    def max_over_ranks(v):
+        if not dist_on:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(flag):
+        if not dist_on:
+            return bool(flag)
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() == 1.0)
+
+    def r4(v):
+        return float(f"{v:.5g}")
 
     # ---- headline: config 2, ELL, one 16.7 M-row band per rank (weak scaling) -----------------
     log("config 2: build + ELL headline")
@@ -305,6 +319,7 @@ def run_product_arm(args):
     x_touched = n_loc + 2 * GRID if world > 1 else n_cols   # a band only reads its rows +- one grid line of x
     ell_bytes = 8 * n_loc * 5 + 4 * x_touched + 4 * n_loc
     csr_bytes = 8 * ci.numel() + 4 * (n_loc + 1) + 4 * x_touched + 4 * n_loc
+    nnz_total = 5 * n_loc * world - 2 * GRID - 2 * GRID * world
 
     def ell_step():
         rc = sp.lib.spmv_b200_spmv_ell_async(E, sp.dptr(x), sp.dptr(y), C.c_void_p(s_ptr))
@@ -326,14 +341,15 @@ def run_product_arm(args):
     ms_per_step = ms / args.steps
     value = world * ell_bytes / (ms_per_step * 1e-3) / 1e9
     launch_gbs = ell_bytes / (ms_per_step * 1e-3) / 1e9
+    y_device_path = y.clone()
 
-    # ---- e2e: blocking C-ABI call with host x / y (pinned), copies inside the timed region -----
+    # ---- e2e: the C-ABI call that takes HOST x / y (pinned); H2D, kernel, D2H inside the timed region ---
     log("e2e")
     x_host = x.cpu().pin_memory()
     y_host = torch.empty(n_loc, dtype=torch.float32).pin_memory()
     res = sp.SpMVResult()
 
-    def e2e_step():
+    def e2e_serial_step():  # what a caller of the reference writes: cudaMemcpy up, spmv_ell, cudaMemcpy down
         x.copy_(x_host, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         rc = sp.lib.spmv_b200_spmv_ell(E, sp.dptr(x), sp.dptr(y), None, n_cols, C.byref(res))
@@ -341,64 +357,86 @@ def run_product_arm(args):
         y_host.copy_(y, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    for _ in range(2):
-        e2e_step()
-    if dist_on:
-        dist.barrier()
-    torch.cuda.synchronize()
+    host_plan = C.c_void_p()
+    assert sp.lib.spmv_b200_ell_host_plan_create(E, 0, C.byref(host_plan)) == 0
+
+    def e2e_step():  # blocking: returns when y_host is complete
+        rc = sp.lib.spmv_b200_spmv_ell_host(host_plan, x_host.data_ptr(), y_host.data_ptr())
+        assert rc == 0
+
+    def wall_time(fn, steps):
+        for _ in range(2):
+            fn()
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return max_over_ranks((time.perf_counter() - t0) / steps)
+
     e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_sec = (time.perf_counter() - t0) / e2e_steps
-    if dist_on:
-        t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_sec = float(t.item())
+    y_host.zero_()
+    e2e_sec = wall_time(e2e_step, e2e_steps)
+    e2e_same = bool(torch.equal(y_host.view(torch.int32), y_device_path.cpu().view(torch.int32)))
+    serial_sec = wall_time(e2e_serial_step, e2e_steps)
+    sp.lib.spmv_b200_ell_host_plan_destroy(host_plan)
     e2e = {"value": world * ell_bytes / e2e_sec / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * n_cols,
            "d2h_bytes_per_step": 4 * n_loc, "ms_per_step": e2e_sec * 1e3,
-           "api": "spmv_b200_spmv_ell (blocking C ABI) + pinned H2D of x + D2H of y"}
+           "api": "spmv_b200_spmv_ell_host (blocking C ABI, pinned host x -> pinned host y; H2D / kernel / D2H "
+                  "pipelined over row chunks on three streams)",
+           "bit_identical_to_device_path": e2e_same,
+           "serial_ms_per_step": serial_sec * 1e3}
+    parity["e2e_host_call_bit_identical"] = e2e_same
 
-    # ---- CPU baseline (rank 0, N = 1): the reference's spmv_cpu_ell on the same matrix ---------
+    # ---- CPU baseline (rank 0, N = 1): the reference's spmv_cpu_ell on the same matrix; its y is the parity check
     log("cpu baseline")
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         reps = 3
-        sec, kind, threads = cpu_reference_time(rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy(),
-                                                x_host.numpy(), n_loc, n_cols, reps)
+        sec, kind, threads, y_cpu = cpu_reference_time(rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy(),
+                                                       x_host.numpy(), n_loc, n_cols, reps)
+        same = bool(np.array_equal(y_cpu.view(np.uint32), y_device_path.cpu().numpy().view(np.uint32)))
+        parity["config2_ell_bit_identical_to_cpu_" + kind] = same
         cpu_baseline = {"value": ell_bytes / sec / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
-                        "ms_per_step": sec * 1e3, "host_cpus": os.cpu_count(),
+                        "ms_per_step": sec * 1e3, "host_cpus": os.cpu_count(), "parity_checked": same,
                         "sample": f"the full config-2 matrix, {reps} passes of spmv_cpu_ell after 1 warm-up "
                                   "(single-threaded: the reference has no threading)"}
 
-    # ---- extra: the CSR kernels on config 2 -----------------------------------------------------
-    log("config 2: CSR kernels")
-    if not args.quick and not args.only_pagerank:
+    # ---- extra: the CSR kernels on config 2 (the selector sends this matrix to VECTOR_CSR) --------------
+    if not args.quick and not args.only_pagerank and world == 1:
+        log("config 2: CSR kernels")
         for kernel, name in ((sp.VECTOR_CSR, "csr_vector"), (sp.SCALAR_CSR, "csr_scalar"), (sp.MERGE_PATH, "csr_merge")):
             cfg = sp.make_config(kernel)
             r = bench_kernel(torch, sp, stream, lambda: sp.lib.spmv_b200_spmv_csr_async(
                 A.ptr, sp.dptr(x), sp.dptr(y), C.byref(cfg), C.c_void_p(s_ptr)), csr_bytes, args.steps, args.warmup,
                 dist_on, world)
-            extra[f"config2_{name}"] = {"gbs": r["gbs"], "ms": r["ms_per_step"], "frac_of_measured_peak": r["gbs"] / world / peak,
-                                        "frac_of_8000": r["gbs"] / world / 8000.0, "bytes": csr_bytes}
+            torch.cuda.synchronize()
+            entry = {"gbs": r4(r["gbs"]), "ms": r4(r["ms_per_step"]), "frac": r4(r["gbs"] / world / peak),
+                     "frac_of_8000": r4(r["gbs"] / world / 8000.0)}
+            if kernel != sp.MERGE_PATH:  # sequential order: bit-identical to the ELL result (= spmv_cpu_*)
+                entry["bit_identical_to_ell"] = bool(torch.equal(y.view(torch.int32), y_device_path.view(torch.int32)))
+                parity[f"config2_{name}_bit_identical"] = entry["bit_identical_to_ell"]
+            extra[f"config2_{name}"] = entry
+        scalars["config2_csr_frac"] = extra["config2_csr_vector"]["frac"]
+        scalars["config2_csr_ms"] = extra["config2_csr_vector"]["ms"]
         # the same matrix through a CSR plan: no hub worth a table, >= 4 non-zeros per row -> the
         # segmented-stream kernel (csr_seg_kernels.cu)
         plan2 = sp.CsrPlan(A.ptr)
         r = bench_kernel(torch, sp, stream, lambda: plan2.spmv(x, y, s_ptr), csr_bytes, args.steps, args.warmup, dist_on, world)
-        extra["config2_csr_planned"] = {"gbs": r["gbs"], "ms": r["ms_per_step"], "frac_of_measured_peak": r["gbs"] / world / peak,
-                                        "frac_of_8000": r["gbs"] / world / 8000.0, "bytes": csr_bytes, "plan_mode": plan2.info()[2]}
+        extra["config2_csr_planned"] = {"gbs": r4(r["gbs"]), "ms": r4(r["ms_per_step"]), "frac": r4(r["gbs"] / world / peak),
+                                        "plan_mode": plan2.info()[2]}
         plan2.close()
         # and with the caller's permission to snapshot the values: the plan re-lays the matrix out as ELL
         plan3 = sp.CsrPlan(A.ptr, snapshot_values=True)
         r = bench_kernel(torch, sp, stream, lambda: plan3.spmv(x, y, s_ptr), csr_bytes, args.steps, args.warmup, dist_on, world)
         extra["config2_csr_planned_value_snapshot"] = {
-            "gbs": r["gbs"], "ms": r["ms_per_step"], "frac_of_measured_peak": r["gbs"] / world / peak,
-            "frac_of_8000": r["gbs"] / world / 8000.0, "bytes": csr_bytes, "plan_mode": plan3.info()[2],
+            "gbs": r4(r["gbs"]), "ms": r4(r["ms_per_step"]), "frac": r4(r["gbs"] / world / peak), "plan_mode": plan3.info()[2],
             "note": "CSR algorithmic bytes over the time of the ELL kernel the plan routes to (it moves 805 MB)"}
         plan3.close()
     sp.ell_destroy(E)
-    del A, rp, ci, va, x, y, x_host, y_host
+    del A, rp, ci, va, x, y, x_host, y_host, y_device_path
     torch.cuda.empty_cache()
 
     if not args.quick and not args.only_pagerank and world == 1:
@@ -414,165 +452,239 @@ def run_product_arm(args):
             cfg = sp.make_config(kernel)
             r = bench_kernel(torch, sp, stream, lambda: sp.lib.spmv_b200_spmv_csr_async(
                 A3.ptr, sp.dptr(x3), sp.dptr(y3), C.byref(cfg), C.c_void_p(s_ptr)), b3, max(5, args.steps // 2), 3)
-            extra[f"config3_{name}"] = {"gbs": r["gbs"], "ms": r["ms_per_step"], "frac_of_measured_peak": r["gbs"] / peak,
-                                        "frac_of_8000": r["gbs"] / 8000.0, "bytes": b3, "rows": rows3, "nnz": ci3.numel()}
+            extra[f"config3_{name}"] = {"gbs": r4(r["gbs"]), "ms": r4(r["ms_per_step"]), "frac": r4(r["gbs"] / peak),
+                                        "rows": rows3, "nnz": ci3.numel()}
         extra["config3_selector"] = "MERGE_PATH (outlier override; reference policy: SCALAR_CSR)"
+        scalars["config3_merge_frac"] = extra["config3_csr_merge"]["frac"]
         del A3, rp3, ci3, va3, x3, y3
         torch.cuda.empty_cache()
 
-    # ---- config 4 / 5: R-MAT SpMV (merge-path) and PageRank, row-sharded over the ranks -----------
-    def rmat_section(scale, seed, do_vector, do_pagerank, relabelled=False):
-        log(f"R-MAT scale {scale}: build" + (" (relabelled vertices)" if relabelled else ""))
-        tag = "_relabelled" if relabelled else ""
-        # SpMV shards balance the merge items (rows + nnz); a PageRank shard also updates and sends
-        # every owned row, so rows weigh more there (8 GPUs, multicast exchange: weight 1 / 4 / 8 ->
-        # 995 / 1063 / 920 iter/s; with unicast peer stores 8 was best, profiles/)
-        weight = args.row_weight if args.row_weight >= 0 else (1 if not do_pagerank or world == 1 or relabelled else 4)
-        n, bounds, srp, sci, sva, n_edges = build_rmat_shard(torch, gen, scale, 16, seed, rank, world, dev,
-                                                            row_weight=weight, relabelled=relabelled)
+    # ---- config 4: R-MAT SpMV through MERGE_PATH, row-sharded over the ranks (strong scaling) ------------
+    def rmat_spmv_section(scale, seed):
+        log(f"R-MAT scale {scale}: build")
+        n, bounds, srp, sci, sva, n_edges = gen.rmat_pagerank_shard(scale, 16, seed, rank, world, dev, row_weight=1)
         torch.cuda.synchronize()
-        shard = D.CudaShard(n, bounds[rank], srp, sci, sva, stream=s_ptr)
-        xg = torch.full((n,), 1.0 / n, dtype=torch.float32, device=dev)
-        yg = torch.empty(n, dtype=torch.float32, device=dev)
         rows_p = bounds[rank + 1] - bounds[rank]
+        csr = sp.DeviceCSR(rows_p, n, srp, sci, sva)
+        xg = torch.full((n,), 1.0 / n, dtype=torch.float32, device=dev)
+        y_slice = torch.empty(max(rows_p, 1), dtype=torch.float32, device=dev)
         b4 = 8 * sci.numel() + 4 * (rows_p + 1) + 4 * n + 4 * rows_p
         tot4 = torch.tensor([float(b4)], dtype=torch.float64, device=dev)
         if dist_on:
             dist.all_reduce(tot4)
-        kernels = [(sp.MERGE_PATH, "csr_merge")] + ([(sp.VECTOR_CSR, "csr_vector")] if do_vector else [])
-        for kernel, name in kernels:
-            log(f"R-MAT scale {scale}: {name}")
-            r = bench_kernel(torch, sp, stream, lambda: shard.spmv(xg, yg, kernel), 0, max(5, args.steps // 2), 3, dist_on)
-            gbs = float(tot4.item()) / (r["ms_per_step"] * 1e-3) / 1e9
-            extra[f"rmat{scale}{tag}_{name}"] = {"gbs": gbs, "ms": r["ms_per_step"], "frac_of_measured_peak": gbs / world / peak,
-                                            "frac_of_8000": gbs / world / 8000.0, "bytes_all_ranks": float(tot4.item()),
-                                            "nnz": n_edges, "rows": n, "scaling": "strong (one graph, row shards)"}
+        tot = float(tot4.item())
+        cfg = sp.make_config(sp.MERGE_PATH)
+        log(f"R-MAT scale {scale}: csr_merge")
+        r = bench_kernel(torch, sp, stream, lambda: sp.lib.spmv_b200_spmv_csr_async(
+            csr.ptr, sp.dptr(xg), sp.dptr(y_slice), C.byref(cfg), C.c_void_p(s_ptr)), 0, max(5, args.steps // 2), 3, dist_on)
+        gbs = tot / (r["ms_per_step"] * 1e-3) / 1e9
+        extra[f"rmat{scale}_csr_merge"] = {"gbs": r4(gbs), "ms": r4(r["ms_per_step"]), "frac": r4(gbs / world / peak),
+                                           "nnz": n_edges, "rows": n, "scaling": "strong (one graph, row shards)"}
+        torch.cuda.synchronize()
+        y_ref = y_slice.clone()
         # the same product through a CSR plan: merge coordinates computed once + hub-column table
         # (csr_hot_kernels.cu) for scale-free shards; bit-identical results, checked here on the full-size shard
         log(f"R-MAT scale {scale}: csr_merge through a CSR plan")
-        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        plan = sp.CsrPlan(shard.csr.ptr)
+        plan = sp.CsrPlan(csr.ptr)
         torch.cuda.synchronize()
         plan_ms = (time.perf_counter() - t0) * 1e3
         hot_columns, hot_nnz, hot_mode = plan.info()
-        y_slice = yg[bounds[rank]:bounds[rank] + rows_p]
-        y_ref = y_slice.clone()  # left by the plain merge-path run above (or the vector kernel)
-        shard.spmv(xg, yg, sp.MERGE_PATH)
-        torch.cuda.synchronize()
-        y_ref.copy_(y_slice)
         r = bench_kernel(torch, sp, stream, lambda: plan.spmv(xg, y_slice, s_ptr), 0, max(5, args.steps // 2), 3, dist_on)
         torch.cuda.synchronize()
-        same = bool(torch.equal(y_ref.view(torch.int32), y_slice.view(torch.int32)))
-        gbs = float(tot4.item()) / (r["ms_per_step"] * 1e-3) / 1e9
-        extra[f"rmat{scale}{tag}_csr_merge_hub_plan"] = {
-            "gbs": gbs, "ms": r["ms_per_step"], "frac_of_measured_peak": gbs / world / peak, "frac_of_8000": gbs / world / 8000.0,
-            "bytes_all_ranks": float(tot4.item()), "hub_columns_rank0": hot_columns,
-            "hub_nnz_fraction_rank0": hot_nnz / max(sci.numel(), 1), "plan_mode": hot_mode, "plan_build_ms": plan_ms,
-            "bit_identical_to_csr_merge": same, "scaling": "strong (one graph, row shards)"}
+        same = all_ok(bool(torch.equal(y_ref.view(torch.int32), y_slice.view(torch.int32))))
+        gbs = tot / (r["ms_per_step"] * 1e-3) / 1e9
+        extra[f"rmat{scale}_csr_merge_plan"] = {
+            "gbs": r4(gbs), "ms": r4(r["ms_per_step"]), "frac": r4(gbs / world / peak), "hub_columns_rank0": hot_columns,
+            "hub_nnz_fraction_rank0": r4(hot_nnz / max(sci.numel(), 1)), "plan_mode": hot_mode, "plan_build_ms": r4(plan_ms),
+            "bit_identical_to_csr_merge": same}
+        parity[f"rmat{scale}_plan_bit_identical_to_merge"] = same
+        scalars[f"rmat{scale}_merge_ms"] = r4(r["ms_per_step"])
+        scalars[f"rmat{scale}_merge_gbs"] = r4(gbs)
+        scalars[f"rmat{scale}_merge_frac"] = r4(gbs / world / peak)
         plan.close()
-        del y_ref
-        if do_pagerank:
-            hub_cols = shard.set_hot(-1)
-            # fixed number of iterations of the sharded loop (stop rule evaluated every iteration,
-            # one iteration late), wall clock around the loop after a device sync, max over ranks
-            shard.damping = 0.85
-            modes = (["multicast", "p2p"] if relabelled else ["multicast", "p2p", "nccl"]) if dist_on else ["single"]
-            with torch.cuda.stream(stream):
-                shard.setup_dangling()
-            have_multicast = False
-            for mode in modes:
-                log(f"R-MAT scale {scale}: PageRank ({mode})")
-                with torch.cuda.stream(stream):
-                    if mode == "multicast":
-                        pair = shard.enable_multicast_exchange()
-                        if pair is None:
-                            log("  no NVSwitch multicast on this box / torch build: " + getattr(shard, "_multicast_error", "multicast_ptr == 0"))
-                            continue
-                        have_multicast = True
-                        r_a, r_b = pair
-                    elif mode == "p2p":
-                        r_a, r_b = shard.enable_peer_exchange()
-                    else:
-                        r_a = torch.empty(n, dtype=torch.float32, device=dev)
-                        r_b = torch.empty_like(r_a)
-                    partial = torch.zeros(3, dtype=torch.float64, device=dev)
-                    shard.init_vector(r_a)
-                    D.pagerank_loop(shard, r_a, r_b, partial, bounds, 0.85, 0.0, 0, fixed_iterations=3)  # warm-up
-                    shard.init_vector(r_a)
-                    if dist_on:
-                        dist.barrier()
-                    torch.cuda.synchronize()
-                    iters = args.pr_iters
-                    t0 = time.perf_counter()
-                    fin, done, residual, conv, l1 = D.pagerank_loop(shard, r_a, r_b, partial, bounds, 0.85, 0.0, 0,
-                                                                    fixed_iterations=iters)
-                    torch.cuda.synchronize()
-                    sec = time.perf_counter() - t0
-                if dist_on:
-                    t = torch.tensor([sec], dtype=torch.float64, device=dev)
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                    sec = float(t.item())
-                    dist.barrier()
-                if mode == "p2p":
-                    shard.disable_peer_exchange()
-                if mode == "multicast":
-                    shard.disable_multicast_exchange()
-                it_bytes = float(tot4.item())
-                exchange = {"multicast": "fused into the step kernel: ONE NVSwitch-multicast store (multimem.st) per finished "
-                                         "row value, delivered to all GPUs by the switch (torch symmetric memory) "
-                                         "+ NCCL all-reduce of 3 f64",
-                            "p2p": "fused into the step kernel: peer stores of finished rows over NVLink (CUDA IPC) "
-                                   "+ NCCL all-reduce of 3 f64",
-                            "nccl": "NCCL all-gather of the rank slices + all-reduce of 3 f64",
-                            "single": "none (1 GPU)"}[mode]
-                key = {"multicast": "pagerank", "single": "pagerank", "nccl": "pagerank_nccl_allgather",
-                       "p2p": "pagerank_p2p_unicast" if have_multicast else "pagerank"}[mode]
-                extra[key + tag] = {
-                    "iters_per_s": iters / sec, "ms_per_iter": sec / iters * 1e3,
-                    "graph": f"R-MAT scale {scale} x16, d=0.85" + (", vertex ids relabelled (Graph500-style)" if relabelled
-                                                                   else ", no vertex permutation"), "n": n, "nnz": n_edges, "iterations_timed": iters,
-                    "l2_residual_after": residual, "effective_gbs": it_bytes / (sec / iters) / 1e9, "scaling": "strong",
-                    "frac_of_measured_peak": it_bytes / (sec / iters) / 1e9 / world / peak, "exchange": exchange,
-                    "hub_columns_rank0": hub_cols, "partition": f"work(row) = nnz + {weight}", "rows_per_rank_max": int(max(bounds[i + 1] - bounds[i] for i in range(world))),
-                    "includes": "fused step + exchange + lagged host read of the residual every iteration; "
-                                "excluded: setup + final normalisation"}
-                del r_a, r_b
-        shard.close()
-        del shard, srp, sci, sva, xg, yg
+        del csr, srp, sci, sva, xg, y_slice, y_ref
         torch.cuda.empty_cache()
 
-    if not args.quick and not args.only_pagerank:
-        rmat_section(args.rmat_scale, 44, do_vector=(world == 1), do_pagerank=(args.pr_scale == args.rmat_scale))
-        if args.pr_scale != args.rmat_scale:
-            rmat_section(args.pr_scale, 45, do_vector=False, do_pagerank=True)
-    if args.only_pagerank:
-        rmat_section(args.pr_scale, 45, do_vector=False, do_pagerank=True)
-    if args.relabelled and (not args.quick or args.only_pagerank):
-        rmat_section(args.pr_scale, 45, do_vector=False, do_pagerank=True, relabelled=True)
+    # ---- config 5: PageRank through the native sharded path (spmv_b200_pr_dist_*) ------------------------
+    names = {"multicast": D.EXCHANGE_MULTICAST, "p2p": D.EXCHANGE_P2P, "nccl": D.EXCHANGE_NCCL}
+
+    def pagerank_parity_small(scale=20, seed=45, iters=10):
+        """Every transport on a scale-20 graph against the f64-accumulator restatement of the reference
+        recurrence (oracle/, checker use only) at equal iteration count: L1 <= 1e-6, transports bit-identical."""
+        log(f"parity: sharded PageRank at scale {scale} against the oracle")
+        n, bounds, srp, sci, sva, _ = gen.rmat_pagerank_shard(scale, 16, seed, rank, world, dev, row_weight=4)
+        torch.cuda.synchronize()
+        csr = sp.DeviceCSR(bounds[rank + 1] - bounds[rank], n, srp, sci, sva)
+        c = comm if dist_on else D.NativeComm(0, 1, session + "-p")
+        vectors, used = {}, {}
+        for name in (["multicast", "p2p", "nccl"] if dist_on else ["p2p"]):
+            pr = D.NativeShardedPageRank(c, csr, bounds[rank], n, names[name])
+            pr.run(0.85, 0.0, 0, fixed_iterations=iters)
+            vectors[name] = pr.ranks(dev).clone()
+            used[name] = D.EXCHANGE_NAMES[pr.exchange]
+            pr.close()
+        if not dist_on:
+            c.close()
+        keys = list(vectors)
+        identical = all_ok(all(torch.equal(vectors[keys[0]].view(torch.int32), vectors[k].view(torch.int32)) for k in keys[1:]))
+        l1 = -1.0
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from oracle_binding import Oracle
+            orc = Oracle()
+            _, frp, fci, fva = gen.rmat_pagerank_csr(scale, 16, seed, "cpu")
+            o_ranks = orc.pagerank_f64(n, n, frp.numpy(), fci.numpy(), fva.numpy(), 0.85, 1e-6, 100, fixed_it=iters)[0]
+            l1 = max(float(np.abs(vectors[k].cpu().numpy().astype(np.float64) - o_ranks).sum()) for k in keys)
+        ok = all_ok(identical and (rank != 0 or l1 <= 1e-6))
+        parity["pagerank_scale20"] = {"l1_vs_oracle_f64_max_over_transports": l1, "tolerance": 1e-6, "iterations": iters,
+                                      "transports": used, "transports_bit_identical": identical, "ok": ok}
+        return ok
+
+    def pagerank_section(scale, seed, relabelled=False):
+        tag = "_relabelled" if relabelled else ""
+        graph_name = f"R-MAT scale {scale} x16, d=0.85" + (", vertex ids relabelled (Graph500-style)" if relabelled
+                                                          else ", no vertex permutation")
+        # a PageRank shard also updates and sends every owned row, so rows weigh more than in plain SpMV
+        weight = args.row_weight if args.row_weight >= 0 else (1 if world == 1 or relabelled else 4)
+        log(f"PageRank {graph_name}: build shard (work(row) = nnz + {weight})")
+        n, bounds, srp, sci, sva, n_edges = gen.rmat_pagerank_shard(scale, 16, seed, rank, world, dev, row_weight=weight,
+                                                                    relabelled=relabelled)
+        torch.cuda.synchronize()
+        rows_p = bounds[rank + 1] - bounds[rank]
+        csr = sp.DeviceCSR(rows_p, n, srp, sci, sva)
+        it_bytes = 8 * sci.numel() + 4 * (rows_p + 1) + 4 * n + 4 * rows_p
+        tot = torch.tensor([float(it_bytes)], dtype=torch.float64, device=dev)
+        if dist_on:
+            dist.all_reduce(tot)
+        it_bytes = float(tot.item())
+        c = comm if dist_on else D.NativeComm(0, 1, session + "-s" + tag)
+        modes = ["p2p"] if not dist_on else (["multicast"] if relabelled else ["nccl", "p2p", "multicast"])
+        iters = args.pr_iters
+        best = None
+        checks = {}
+        for mode in modes:
+            log(f"PageRank {graph_name}: {mode}")
+            pr = D.NativeShardedPageRank(c, csr, bounds[rank], n, names[mode])
+            used = D.EXCHANGE_NAMES[pr.exchange] if dist_on else "none (1 GPU)"
+            sec = None
+            for _ in range(2):  # the first run also builds the dangling set and captures the CUDA graphs
+                res = pr.run(0.85, 0.0, 0, fixed_iterations=iters)
+                t = max_over_ranks(res.device_seconds)
+                sec = t if sec is None else min(sec, t)
+            vec = pr.ranks(dev)
+            total = float(vec.double().sum().item())
+            checks[mode] = vector_checksum(torch, vec) + (total,)
+            entry = {"iters_per_s": r4(iters / sec), "ms_per_iter": r4(sec / iters * 1e3), "exchange": used,
+                     "graph": graph_name, "n": n, "nnz": n_edges, "iterations_timed": iters,
+                     "l2_residual_after": res.final_residual, "effective_gbs": r4(it_bytes / (sec / iters) / 1e9),
+                     "frac": r4(it_bytes / (sec / iters) / 1e9 / world / peak), "cuda_graph_replay": bool(res.graph_replay),
+                     "kernels_per_iteration": res.kernels_per_iteration, "hub_columns_rank0": pr.hub_columns,
+                     "partition": f"work(row) = nnz + {weight}",
+                     "rows_per_rank_max": int(max(bounds[i + 1] - bounds[i] for i in range(world))),
+                     "timing": "CUDA events around the whole loop on every rank (inside spmv_b200_pr_dist_run), max over ranks; "
+                               "excluded: set-up and the final normalisation"}
+            extra[f"pagerank{tag}_{mode}" if dist_on else f"pagerank{tag}"] = entry
+            if best is None or entry["iters_per_s"] > best[1]["iters_per_s"]:
+                best = (mode, entry)
+            pr.close()
+        if not dist_on:
+            c.close()
+        # full-size parity: every rank holds the bit-identical vector, whatever the transport, and it sums to 1
+        mine = torch.tensor([v for m in modes for v in checks[m][:2]], dtype=torch.int64, device=dev)
+        ok = True
+        if dist_on:
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            ok = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+        first = checks[modes[0]]
+        same_transports = all(checks[m][:2] == first[:2] for m in modes)
+        sum_ok = abs(first[2] - 1.0) <= 1e-6
+        ok = all_ok(ok and same_transports and sum_ok)
+        parity[f"pagerank_scale{scale}{tag}"] = {"ranks_bit_equal_across_gpus": ok if dist_on else None,
+                                                  "transports_bit_identical": same_transports, "sum_of_ranks": first[2],
+                                                  "ok": ok}
+        del csr, srp, sci, sva
+        torch.cuda.empty_cache()
+        return best
+
+    def pagerank_one_gpu(scale, seed):
+        """The same graph, whole, on rank 0's GPU alone (the other ranks wait): the denominator of the
+        1 -> N scaling figure, measured in the same run on the same box."""
+        sec = 0.0
+        if rank == 0:
+            log(f"PageRank R-MAT {scale} on ONE GPU (scaling denominator)")
+            n, bounds, srp, sci, sva, _ = gen.rmat_pagerank_shard(scale, 16, seed, 0, 1, dev, row_weight=1)
+            torch.cuda.synchronize()
+            csr = sp.DeviceCSR(n, n, srp, sci, sva)
+            c1 = D.NativeComm(0, 1, session + "-one")
+            pr = D.NativeShardedPageRank(c1, csr, 0, n, D.EXCHANGE_P2P)
+            for _ in range(2):
+                res = pr.run(0.85, 0.0, 0, fixed_iterations=args.pr_iters)
+                sec = res.device_seconds if sec == 0.0 else min(sec, res.device_seconds)
+            pr.close()
+            c1.close()
+            del csr, srp, sci, sva
+            torch.cuda.empty_cache()
+        if dist_on:
+            dist.barrier()
+        return max_over_ranks(sec)
+
+    parity_ok = True
+    if not args.quick:
+        if not args.only_pagerank:
+            rmat_spmv_section(args.rmat_scale, 44)
+        parity_ok = pagerank_parity_small() and parity_ok
+        best = pagerank_section(args.pr_scale, 45)
+        scalars["pagerank_iters_per_s"] = best[1]["iters_per_s"]
+        scalars["pagerank_ms_per_iter"] = best[1]["ms_per_iter"]
+        scalars["pagerank_exchange"] = best[0] if dist_on else "none (1 GPU)"
+        scalars["pagerank_frac"] = best[1]["frac"]
+        if dist_on:
+            for mode in ("nccl", "p2p", "multicast"):
+                e = extra.get(f"pagerank_{mode}")
+                if e:
+                    scalars[f"pagerank_{mode}_iters_per_s"] = e["iters_per_s"]
+            if args.pr_one_gpu:
+                one = pagerank_one_gpu(args.pr_scale, 45)
+                scalars["pagerank_1gpu_iters_per_s"] = r4(args.pr_iters / one)
+                scalars["pagerank_1gpu_ms_per_iter"] = r4(one / args.pr_iters * 1e3)
+                scalars["pagerank_speedup_vs_1gpu"] = r4(best[1]["iters_per_s"] / (args.pr_iters / one))
+        else:
+            scalars["pagerank_1gpu_iters_per_s"] = best[1]["iters_per_s"]
+        if args.relabelled:
+            best_r = pagerank_section(args.pr_scale, 45, relabelled=True)
+            scalars["pagerank_relabelled_iters_per_s"] = best_r[1]["iters_per_s"]
+    parity_ok = parity_ok and all(v.get("ok", True) if isinstance(v, dict) else bool(v) for v in parity.values())
+    parity["ok"] = parity_ok
 
     if rank == 0:
+        traffic, traffic_src = ncu_traffic_for("ell_tma_pipe_kernel<1>") if world == 1 else (None, "N > 1: not captured")
+        if args.ncu_traffic is not None:
+            traffic, traffic_src = args.ncu_traffic, "--ncu-traffic"
         roofline = {"bound": "hbm", "achieved": launch_gbs, "peak": peak, "unit": "GB/s", "frac": launch_gbs / peak,
                     "peak_source": peak_src, "frac_of_8000_nominal": launch_gbs / 8000.0,
                     "kernel": "ell_tma_pipe_kernel<1>", "algorithmic_bytes_per_launch": ell_bytes,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of ell_tma_pipe_kernel<1> on this workload, one
-                    # `ncu --set full` capture (profiles/r1_ell_tma_pipe_c2_raw.csv: 738.8 + 61.9 MB; y is
-                    # partly still in L2 at kernel end, hence slightly below the 805.3 MB algorithmic)
-                    "traffic": args.ncu_traffic if args.ncu_traffic is not None else (800728576.0 if world == 1 else None)}
+                    "traffic": traffic, "traffic_source": traffic_src}
+        config = headline_config(n_loc * world, nnz_total, ell_bytes * world, world)
+        config.update(scalars)
         line = {
             "metric": "spmv_effective_hbm_gbs", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config2: 5-point Laplacian 4096x4096 grid per GPU (16.7M rows, 83.9M nnz), ELL width 5, "
-                                   "spmv_ell; x = hash U[-1,1)", "rows_per_gpu": n_loc, "bytes_per_step_per_gpu": ell_bytes,
-                       "l2": "inputs (805 MB/GPU) larger than L2, no flush", "parallelism": f"row shards x{world}, x replicated"},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "extra": extra,
+            "cpu_baseline": cpu_baseline, "parity": parity,
         }
+        line.update(scalars)
+        line["extra"] = extra
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
+    if not parity_ok:
+        raise SystemExit("bench.py: PARITY FAILURE -- " + json.dumps(parity))
 
 
 def main():
@@ -592,8 +704,11 @@ def main():
     ap.add_argument("--relabelled", type=int, default=1,
                     help="also run PageRank on the same R-MAT graph with relabelled vertex ids (extra.pagerank_relabelled)")
     ap.add_argument("--ncu-traffic", type=float, default=None,
-                    help="dram bytes per launch of the dominant kernel from an ncu capture (default: the committed one, "
+                    help="dram bytes per launch of the dominant kernel from an ncu capture (default: profiles/ncu_traffic.json, "
                          "N = 1 only)")
+    ap.add_argument("--pr-one-gpu", type=int, default=1,
+                    help="N > 1: rank 0 also runs the whole PageRank graph on its GPU alone (pagerank_1gpu_iters_per_s, "
+                         "pagerank_speedup_vs_1gpu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

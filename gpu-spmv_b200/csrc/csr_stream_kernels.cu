@@ -488,152 +488,141 @@ csr_pipe_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* 
 }
 
 // ------------------------------------------------------------------------------------------
-// csr_prod_kernel -- SCALAR_CSR / one-lane VECTOR_CSR for matrices of SHORT rows: the same
-// persistent TMA ring as csr_pipe_kernel (row_ptrs window + aligned value / column spans per stage),
-// but the window is consumed in two coalesced phases instead of by row owners walking their rows:
-//
-//   1. products IN PLACE, in stream order: thread t takes staged slots t, t + 256, ... and overwrites
-//      the value slot with value * x[col] (__fmul_rn).  Consecutive lanes read consecutive slots (no
-//      bank conflicts, no per-element bounds: every staged slot is a real non-zero of the matrix) and
-//      their x gathers touch neighbouring columns of neighbouring rows;
-//   2. after one barrier, thread r sums the products of row r front to back (__fadd_rn).
-//
-// Per row this is exactly spmv_cpu_csr's `sum += values[j] * x[col[j]]` with separately rounded
-// multiply and add (reference src/spmv_cpu.cpp:6-16) => bit-identical, like csr_pipe_kernel<1>.
-// Why: ncu of csr_pipe_kernel<1,6,false> on config 2 (profiles/r1_csr_pipe_c2.md) showed it
-// issue-bound -- 45 thread instructions per non-zero, three predicates per element -- with DRAM at
-// 63 %.  Here a non-zero costs ~7 instructions in phase 1 and ~5 in phase 2.
-// Non-zeros that are not staged (the last nnz % 4 of the matrix, or a window that exceeds the stage)
-// are multiplied from global memory by the row that owns them, in the same order.
-constexpr int kProdBatch = 8;  // gathers in flight per thread
+// csr_short_kernel -- SCALAR_CSR / one-lane VECTOR_CSR for matrices of SHORT rows (the reference's
+// thread-per-row kernel, src/spmv_kernels.cu:168-188, and what spmv_auto_config sends the 5-point
+// Laplacian of BASELINE config 2 to): the persistent TMA ring of csr_pipe_kernel (row_ptrs window +
+// aligned value / column spans per stage) consumed by ROW OWNERS with nothing else in the loop.
+// ncu of csr_pipe_kernel<1,6,false> on config 2 (profiles/r1_csr_pipe_c2.md) showed it issue-bound:
+// 45 thread instructions per non-zero (a "staged or global?" branch per element) and 63 registers =
+// 4 CTAs per SM.  Here a window is either entirely staged -- then a row costs one predicate per slot
+// and ~8 instructions per non-zero, in <= 32 registers (8 CTAs = 2048 threads per SM, like the ELL
+// kernel) -- or (CTA-uniform, rare: the matrix tail, a window denser than a stage) its rows are walked
+// from global memory.  Per row this is spmv_cpu_csr's `sum += values[j] * x[col[j]]` front to back
+// with separately rounded multiply and add (reference src/spmv_cpu.cpp:6-16) => bit-identical.
+__device__ __noinline__ void short_rows_from_global(int nr, const int* __restrict__ rp, const int* __restrict__ col_indices,
+                                                    const float* __restrict__ values, const float* __restrict__ x,
+                                                    float* __restrict__ y) {
+    for (int r = threadIdx.x; r < nr; r += kThreads) {
+        const int a = __ldg(rp + r), b = __ldg(rp + r + 1);
+        float acc = 0.0f;
+#pragma unroll 1
+        for (int j = a; j < b; ++j)
+            acc = __fadd_rn(acc, __fmul_rn(dev::ld_stream_f(values + j), dev::ld_x(x + dev::ld_stream_i(col_indices + j))));
+        y[r] = acc;
+    }
+}
 
-__global__ void __launch_bounds__(kThreads)
-csr_prod_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* __restrict__ col_indices,
-                const float* __restrict__ values, const float* __restrict__ x, float* __restrict__ y,
-                int window_rows, int rows_per_thread, int cap, int stages) {
+// Compile-time geometry: RPT rows per thread (window = 256 * RPT rows), CAP staged non-zeros per
+// stage, S stages -- every shared-memory address in the loop is then base + immediate.
+template <int RPT, int CAP>
+struct ShortStage {
+    static constexpr int kWindow = kThreads * RPT;
+    int rp[kWindow + 4];   // row_ptrs[r0 .. r0 + kWindow + 3]
+    float val[CAP];        // values[base .. staged_end)
+    int col[CAP];          // col_indices[base .. staged_end)
+    int base;              // non-zero index held by slot 0
+    int staged;            // 0: the window was not staged (matrix tail / denser than CAP)
+    int pad[2];
+};
+
+template <int U, int RPT, int CAP, int S>
+__global__ void __launch_bounds__(kThreads, (CAP <= 1536 ? 8 : (CAP <= 3072 ? 4 : 2)))
+csr_short_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* __restrict__ col_indices,
+                 const float* __restrict__ values, const float* __restrict__ x, float* __restrict__ y) {
+    using Stage = ShortStage<RPT, CAP>;
+    constexpr int kWindow = Stage::kWindow;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [stages] (<= 16)
-    unsigned char* ring = smem_raw + 128;
-    const size_t stage_bytes = sizeof(PipeStageHeader) + static_cast<size_t>(window_rows + 4) * 4 +
-                               static_cast<size_t>(cap) * 8;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [S]: the stage's bulk copies have landed
+    Stage* ring = reinterpret_cast<Stage*>(smem_raw + 128);
     const int tid = threadIdx.x;
-    const int num_windows = (rows + window_rows - 1) / window_rows;
+    const int num_windows = (rows + kWindow - 1) / kWindow;
 
-    auto stage_header = [&](int s) { return reinterpret_cast<PipeStageHeader*>(ring + s * stage_bytes); };
-    auto stage_rp = [&](int s) { return reinterpret_cast<int*>(ring + s * stage_bytes + sizeof(PipeStageHeader)); };
-    auto stage_val = [&](int s) { return reinterpret_cast<float*>(stage_rp(s) + window_rows + 4); };
-    auto stage_col = [&](int s) { return reinterpret_cast<int*>(stage_val(s) + cap); };
-
-    auto issue = [&](int w, int s, int n0, int n1) {  // thread 0 only
-        const int r0 = w * window_rows;
+    auto issue = [&](int w, int s, int n0, int n1) {  // thread 0 only; [n0, n1) = the window's non-zeros
+        const int r0 = w * kWindow;
         const int base = n0 & ~3;
-        int end = min((n1 + 3) & ~3, nnz & ~3);
-        end = min(end, base + cap);
-        end = max(end, base);
-        const bool rp_ok = r0 + window_rows + 4 <= rows + 1;
-        PipeStageHeader* h = stage_header(s);
-        h->base = base;
-        h->staged_end = end;
-        h->rp_staged = rp_ok ? 1 : 0;
-        h->overflow = 0;
-        const uint32_t nz_bytes = static_cast<uint32_t>(end - base) * 4u;
-        const uint32_t rp_bytes = rp_ok ? static_cast<uint32_t>(window_rows + 4) * 4u : 0u;
-        dev::mbar_arrive_expect_tx(bars + s, 2u * nz_bytes + rp_bytes);
-        if (rp_bytes) dev::tma_bulk_g2s(stage_rp(s), row_ptrs + r0, rp_bytes, bars + s);
+        const int end = (n1 + 3) & ~3;
+        // all or nothing: the window is staged when its row_ptrs can be bulk-copied without
+        // over-reading, its span fits the stage and does not reach into the unaligned matrix tail
+        const bool staged = r0 + kWindow + 4 <= rows + 1 && end - base <= CAP && end <= (nnz & ~3);
+        Stage& st = ring[s];
+        st.base = base;
+        st.staged = staged ? 1 : 0;
+        const uint32_t nz_bytes = staged ? static_cast<uint32_t>(end - base) * 4u : 0u;
+        const uint32_t rp_bytes = staged ? static_cast<uint32_t>(kWindow + 4) * 4u : 0u;
+        dev::mbar_arrive_expect_tx(full + s, 2u * nz_bytes + rp_bytes);
+        if (rp_bytes) dev::tma_bulk_g2s(st.rp, row_ptrs + r0, rp_bytes, full + s);
         if (nz_bytes) {
-            dev::tma_bulk_g2s(stage_val(s), values + base, nz_bytes, bars + s);
-            dev::tma_bulk_g2s(stage_col(s), col_indices + base, nz_bytes, bars + s);
+            dev::tma_bulk_g2s(st.val, values + base, nz_bytes, full + s);
+            dev::tma_bulk_g2s(st.col, col_indices + base, nz_bytes, full + s);
         }
-    };
-    auto window_bounds = [&](int w, int& n0, int& n1) {
-        const int r0 = w * window_rows;
-        n0 = __ldg(row_ptrs + r0);
-        n1 = __ldg(row_ptrs + min(r0 + window_rows, rows));
     };
 
     if (tid == 0) {
-        for (int s = 0; s < stages; ++s) dev::mbar_init(bars + s, 1);
+        for (int s = 0; s < S; ++s) dev::mbar_init(full + s, 1);
         dev::mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0) {
-        for (int s = 0; s < stages; ++s) {
+        for (int s = 0; s < S; ++s) {
             const int w = blockIdx.x + s * gridDim.x;
-            if (w < num_windows) {
-                int n0, n1;
-                window_bounds(w, n0, n1);
-                issue(w, s, n0, n1);
-            }
+            if (w < num_windows) issue(w, s, __ldg(row_ptrs + w * kWindow), __ldg(row_ptrs + min((w + 1) * kWindow, rows)));
         }
     }
 
-    int it = 0;
-    for (int w = blockIdx.x; w < num_windows; w += gridDim.x, ++it) {
-        const int s = it % stages;
-        const uint32_t parity = (it / stages) & 1u;
-        const int next = w + stages * gridDim.x;
+    int s = 0;
+    uint32_t parity = 0;
+    for (int w = blockIdx.x; w < num_windows; w += gridDim.x) {
+        const int next = w + S * gridDim.x;
         int next_n0 = 0, next_n1 = 0;
-        if (tid == 0 && next < num_windows) window_bounds(next, next_n0, next_n1);  // latency hidden by the consume phase
-
-        dev::mbar_wait(bars + s, parity);
-        const PipeStageHeader h = *stage_header(s);
-        int* s_rp = stage_rp(s);
-        float* s_val = stage_val(s);
-        const int* s_col = stage_col(s);
-        const int r0 = w * window_rows;
-        const int nr = min(window_rows, rows - r0);
-        if (!h.rp_staged) {  // last window(s): a bulk copy of window_rows + 4 entries would over-read
-            for (int i = tid; i <= nr; i += kThreads) s_rp[i] = __ldg(row_ptrs + r0 + i);
+        if (tid == 0 && next < num_windows) {  // a DRAM round trip, hidden by this window's consume phase
+            next_n0 = __ldg(row_ptrs + next * kWindow);
+            next_n1 = __ldg(row_ptrs + min((next + 1) * kWindow, rows));
         }
-
-        // ---- phase 1: products in place, stream order ------------------------------------------
-        // every gather of a batch is issued before the first product: one gather latency per window
-        const int n_staged = h.staged_end - h.base;
-        for (int j0 = tid; j0 < n_staged; j0 += kProdBatch * kThreads) {
-            int c[kProdBatch];
-            float xv[kProdBatch];
+        dev::mbar_wait(full + s, parity);
+        const Stage& st = ring[s];
+        const int r0 = w * kWindow;
+        const int nr = min(kWindow, rows - r0);
+        if (st.staged) {
+            const int base = st.base;
 #pragma unroll
-            for (int u = 0; u < kProdBatch; ++u) {
-                const int j = j0 + u * kThreads;
-                if (j < n_staged) c[u] = s_col[j];
-            }
+            for (int i = 0; i < RPT; ++i) {
+                const int r = tid + i * kThreads;
+                if (r < nr) {
+                    const int a = st.rp[r] - base;   // stage slot of the row's first non-zero
+                    const int len = st.rp[r + 1] - base - a;
+                    const float* pv = st.val + a;
+                    const int* pc = st.col + a;
+                    float acc = 0.0f;
+                    for (int j = 0; j < len; j += U) {
+                        int c[U];
+                        float xv[U];
 #pragma unroll
-            for (int u = 0; u < kProdBatch; ++u) {
-                const int j = j0 + u * kThreads;
-                if (j < n_staged) xv[u] = dev::ld_x(x + c[u]);
-            }
+                        for (int u = 0; u < U; ++u)
+                            if (j + u < len) c[u] = pc[j + u];
 #pragma unroll
-            for (int u = 0; u < kProdBatch; ++u) {
-                const int j = j0 + u * kThreads;
-                if (j < n_staged) s_val[j] = __fmul_rn(s_val[j], xv[u]);
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 2: one thread per row, front to back ----------------------------------------
-        const float* s_prod = s_val - h.base;  // s_prod[j] for a global non-zero index j
-        for (int i = 0; i < rows_per_thread; ++i) {
-            const int r = tid + i * kThreads;
-            if (r < nr) {
-                const int a = s_rp[r], b = s_rp[r + 1];
-                float acc = 0.0f;
-                if (b <= h.staged_end && a >= h.base) {
-                    for (int j = a; j < b; ++j) acc = __fadd_rn(acc, s_prod[j]);
-                } else {  // part of the row was not staged (matrix tail / oversized window)
-                    for (int j = a; j < b; ++j) {
-                        const float p = (j >= h.base && j < h.staged_end)
-                                            ? s_prod[j]
-                                            : __fmul_rn(dev::ld_stream_f(values + j), dev::ld_x(x + dev::ld_stream_i(col_indices + j)));
-                        acc = __fadd_rn(acc, p);
+                        for (int u = 0; u < U; ++u)
+                            if (j + u < len) xv[u] = dev::ld_x(x + c[u]);
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if (j + u < len) acc = __fadd_rn(acc, __fmul_rn(pv[j + u], xv[u]));
                     }
+                    y[r0 + r] = acc;
                 }
-                y[r0 + r] = acc;
             }
+        } else {  // not staged: the same rows, the same order, from global memory
+            short_rows_from_global(nr, row_ptrs + r0, col_indices, values, x, y + r0);
         }
-        __syncthreads();  // stage s is free again
+        // A CTA-wide barrier frees the stage.  (Measured alternative: per-stage `empty` mbarriers that
+        // only thread 0 waits on -- 0.168 ms against 0.144 ms on config 2: the warps drift apart and
+        // the refill waits for the slowest anyway.)
+        __syncthreads();
         if (tid == 0 && next < num_windows) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(next, s, next_n0, next_n1);
+        }
+        if (++s == S) {
+            s = 0;
+            parity ^= 1u;
         }
     }
 }
@@ -755,55 +744,49 @@ cudaError_t launch_pipe_lpr(const CsrView& A, const float* x, float* y, cudaStre
     return launch_pipe_lpr_u<LPR, 8, false>(A, x, y, stream);
 }
 
-// Geometry of csr_prod_kernel: windows of 256 * rpt rows holding ~1.3-2.5 K non-zeros.
-void prod_geometry(const CsrView& A, int& rpt, int& cap) {
-    const double avg = static_cast<double>(A.nnz) / A.rows;
-    static const int env_nz = stream_env_int("SPMV_B200_CSR_PROD_WINDOW_NNZ", 1536);
-    rpt = static_cast<int>(env_nz / (avg * kThreads) + 0.5);
-    rpt = rpt < 1 ? 1 : (rpt > 8 ? 8 : rpt);
-    const int window = kThreads * rpt;
-    cap = static_cast<int>(1.125 * avg * window) + 32;
-    cap = (cap + 127) / 128 * 128;
-}
-
-cudaError_t launch_prod(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
-    int rpt, cap;
-    prod_geometry(A, rpt, cap);
-    const int window = kThreads * rpt;
-    static const int env_stages = stream_env_int("SPMV_B200_CSR_STAGES", 0);
+template <int U, int RPT, int CAP>
+cudaError_t launch_short_as(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
+    constexpr int S = 2;  // ring depth: deeper rings leave fewer CTAs per SM (measured: 3 stages 0.166 ms against 0.144 ms)
+    auto kernel = csr_short_kernel<U, RPT, CAP, S>;
+    const size_t smem = 128 + S * sizeof(ShortStage<RPT, CAP>);
     static const int env_ctas = stream_env_int("SPMV_B200_CSR_CTAS_PER_SM", 0);
-    const int stages = env_stages > 1 ? (env_stages > 16 ? 16 : env_stages) : 2;
-    const size_t stage_bytes = sizeof(PipeStageHeader) + static_cast<size_t>(window + 4) * 4 + static_cast<size_t>(cap) * 8;
-    const size_t smem = 128 + stages * stage_bytes;
-    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // caller falls back
-    cudaError_t e = cudaFuncSetAttribute(csr_prod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     int fit = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, csr_prod_kernel, kThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, kernel, kThreads, smem);
     if (e != cudaSuccess) return e;
     if (fit < 1) return cudaErrorInvalidConfiguration;
     const int ctas_per_sm = (env_ctas > 0 && env_ctas < fit) ? env_ctas : fit;
     int sms = 148, dev_id = 0;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    constexpr int window = kThreads * RPT;
     const int num_windows = (A.rows + window - 1) / window;
     int blocks = sms * ctas_per_sm;
     if (blocks > num_windows) blocks = num_windows;
-    csr_prod_kernel<<<blocks, kThreads, smem, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values, x, y, window, rpt,
-                                                        cap, stages);
+    kernel<<<blocks, kThreads, smem, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values, x, y);
     count_launches(1);
     return cudaGetLastError();
 }
 
-// Short rows only: thread r walks row r alone in phase 2, and a window must fit a stage.
-bool prod_eligible(const CsrView& A, cudaStream_t stream) {
-    static const int mode = stream_env_int("SPMV_B200_CSR_PROD", -1);  // 0 off, 1 forced, -1 by structure
+// Geometry by the average row length: a window should hold 1.3-1.5 K non-zeros (measured on config 2:
+// 1024 / 1536 / 2560 per window -> 0.145 / 0.144 / 0.155 ms) with 12.5 % head-room in the stage.
+cudaError_t launch_short(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
+    const double avg = static_cast<double>(A.nnz) / A.rows;
+    if (avg <= 2.6) return launch_short_as<4, 2, 1536>(A, x, y, stream);    // 512-row windows
+    if (avg <= 5.2) return launch_short_as<6, 1, 1536>(A, x, y, stream);    // 256-row windows, 8 CTAs per SM
+    if (avg <= 10.5) return launch_short_as<8, 1, 3072>(A, x, y, stream);   // 4 CTAs per SM
+    return launch_short_as<8, 1, 5120>(A, x, y, stream);                    // up to ~17 per row, 2 CTAs per SM
+}
+
+// Short rows only: a row is walked by one thread, and a window that does not fit a stage is walked
+// from global memory by 256 threads -- both fine while no row is long.
+bool short_eligible(const CsrView& A, cudaStream_t stream) {
+    static const int mode = stream_env_int("SPMV_B200_CSR_SHORT", -1);  // 0 off, 1 forced, -1 by structure
     if (mode == 0) return false;
     if (mode == 1) return true;
     const double avg = static_cast<double>(A.nnz) / A.rows;
-    if (avg > 24.0) return false;
-    int rpt, cap;
-    prod_geometry(A, rpt, cap);
+    if (avg > 16.0) return false;  // launch_short's largest stage
     return longest_row_cached(A, stream) <= 64;
 }
 
@@ -817,8 +800,8 @@ bool pipe_eligible(const CsrView& A) {
 template <int LPR>
 cudaError_t launch_best_lpr(const CsrView& A, const float* x, float* y, cudaStream_t stream) {
     if (pipe_eligible(A)) {
-        if (LPR == 1 && prod_eligible(A, stream)) {
-            const cudaError_t e = launch_prod(A, x, y, stream);
+        if (LPR == 1 && short_eligible(A, stream)) {
+            const cudaError_t e = launch_short(A, x, y, stream);
             if (e != cudaErrorInvalidConfiguration) return e;
         }
         const cudaError_t e = launch_pipe_lpr<LPR>(A, x, y, stream);

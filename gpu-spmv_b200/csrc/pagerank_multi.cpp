@@ -23,8 +23,14 @@ int pagerank_multi(const CSRMatrix* adj, const PageRankConfig* config, int n_gpu
     if (!adj->row_ptrs || (adj->nnz > 0 && (!adj->col_indices || !adj->values)))
         return static_cast<int>(SpMVError::INVALID_FORMAT);  // host arrays are what gets sharded
     if (adj->num_cols != adj->num_rows) return static_cast<int>(SpMVError::INVALID_DIMENSION);
+    // devices == NULL: ranks 0 .. n_gpus-1 on devices 0 .. n_gpus-1.  An explicit list may name a device
+    // more than once (several ranks share a GPU: the peer-store exchange and the flag barrier work
+    // between streams of one device exactly as between devices -- how the sharded path is tested on a
+    // one-GPU box; the multicast and NCCL transports need distinct devices).
     int visible = 0;
-    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < n_gpus) {
+    bool devices_ok = cudaGetDeviceCount(&visible) == cudaSuccess && (devices || visible >= n_gpus);
+    for (int r = 0; devices_ok && devices && r < n_gpus; ++r) devices_ok = devices[r] >= 0 && devices[r] < visible;
+    if (!devices_ok) {
         cudaGetLastError();
         return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     }

@@ -516,7 +516,9 @@ typedef struct {
     int kernels_per_iteration;
 } spmv_b200_pr_dist_result;
 
-/* One process, n_gpus devices (devices == NULL: 0 .. n_gpus-1): adj is a HOST CSR (host arrays);
+/* One process, n_gpus devices (devices == NULL: 0 .. n_gpus-1; an explicit list may name a device
+ * more than once -- several ranks then share that GPU, which the peer-store transport supports):
+ * adj is a HOST CSR (host arrays);
  * shards balance work(row) = nnz + row_weight; ranks_out is a host array of num_rows floats
  * (normalised, as pagerank()).  fixed_iterations > 0 runs exactly that many (no stop rule). */
 SPMV_B200_API int spmv_b200_pagerank_multi(const spmv_b200_csr* adj, const spmv_b200_pagerank_config* config,

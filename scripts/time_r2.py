@@ -1,4 +1,4 @@
-"""Round-2 timing aid (one GPU): config-2 CSR through SCALAR/VECTOR with and without the products-in-place
+"""Round-2 timing aid (one GPU): config-2 CSR through SCALAR/VECTOR with and without the short-row
 kernel, and the pipelined host-buffer ELL call against the serial form.  CUDA-event / wall times; never run under ncu."""
 import ctypes as C
 import os
@@ -36,12 +36,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         print(f"  {os.environ.get('TAG','')} c2 csr {name}: {ms:.4f} ms  {nbytes / ms / 1e6:.0f} GB/s  frac {nbytes / ms / 1e6 / 6548.5:.3f}", flush=True)
     sys.exit(0)
 
-env_sets = [("prod (default)", {}), ("pipe (PROD=0)", {"SPMV_B200_CSR_PROD": "0"}),
-            ("prod window 1024", {"SPMV_B200_CSR_PROD_WINDOW_NNZ": "1024"}),
-            ("prod window 2560", {"SPMV_B200_CSR_PROD_WINDOW_NNZ": "2560"}),
-            ("prod window 4096", {"SPMV_B200_CSR_PROD_WINDOW_NNZ": "4096"}),
-            ("prod 3 stages", {"SPMV_B200_CSR_STAGES": "3"}),
-            ("prod 6 CTAs/SM", {"SPMV_B200_CSR_CTAS_PER_SM": "6"})]
+env_sets = [("short-row ring (default)", {}), ("general ring (SHORT=0)", {"SPMV_B200_CSR_SHORT": "0"}),
+            ("short 6 CTAs/SM", {"SPMV_B200_CSR_CTAS_PER_SM": "6"})]
 if len(sys.argv) > 1 and sys.argv[1] == "csr":
     for tag, env in env_sets:
         e = dict(os.environ, TAG=tag, **env)
