@@ -3,7 +3,7 @@
 // (de)serialisation and row statistics.
 //
 // Pure integer / copy logic; results are bit-identical to the reference
-// (src/csr_matrix.cpp, src/ell_matrix.cpp) -- tests/test_formats_parity.py
+// (src/csr_matrix.cpp, src/ell_matrix.cpp) -- tests/test_host_formats.py
 // checks that against the oracle and against oracle/_ref.
 #include "internal.hpp"
 

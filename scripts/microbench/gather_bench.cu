@@ -150,7 +150,7 @@ int main() {
         fflush(stdout);
     };
     // ---- (a) global
-    for (uint32_t fp : {1u << 18, 1u << 21, 1u << 24, 1u << 26}) {
+    for (uint32_t fp : {1u << 13, 1u << 14, 1u << 15, 1u << 16, 1u << 18, 1u << 21, 1u << 24, 1u << 26}) {
         for (int window : {0, 16, 8, 4, 2}) {
             if (window && fp != (1u << 24)) continue;
             make_idx<<<1184, 256>>>(idx, n, fp, window);
