@@ -134,6 +134,7 @@ PROTOTYPES = {
     "spmv_b200_compare_gpu_cpu_csr": (C.c_int, [CSR_P, c_float_p, CFG_P, BC_P, BR_P, BR_P, c_float_p]),
     "spmv_b200_benchmark_to_json": (C.c_int, [BR_P, C.c_char_p, C.c_int]),
     "spmv_b200_benchmark_from_json": (C.c_int, [C.c_char_p, BR_P]),
+    "spmv_b200_benchmark_csr_report": (C.c_int, [CSR_P, c_float_p, CFG_P, BC_P, C.c_float, C.c_char_p, C.c_int]),
     # E. extensions
     "spmv_b200_version": (C.c_char_p, []),
     "spmv_b200_launch_count": (C.c_ulonglong, []),

@@ -7,7 +7,9 @@
 #include "internal.hpp"
 #include "pagerank_dist.hpp"
 
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <new>
 
 using namespace spmv;
@@ -290,6 +292,49 @@ int spmv_b200_benchmark_from_json(const char* json, spmv_b200_bench_result* out)
         to_c(benchmark_from_json(json), out);
         return 0;
     });
+}
+
+int spmv_b200_benchmark_csr_report(const spmv_b200_csr* A_c, const float* x, const spmv_b200_config* config,
+                                   const spmv_b200_bench_config* bench_config, float peak_gb_s, char* buf, int cap) {
+    const CSRMatrix* A = cpp(A_c);
+    if (!A || !x || !buf || cap <= 0) return kBadArg;
+    if (!A->d_row_ptrs || (A->nnz > 0 && (!A->d_col_indices || !A->d_values))) return SPMV_B200_INVALID_FORMAT;
+    int rc = -1;
+    const int status = guarded([&] {
+        SpMVConfig chosen = config ? *cpp(config) : spmv_auto_config(A);
+        const BenchmarkConfig defaults;
+        const BenchmarkConfig& bc = bench_config ? *cpp(bench_config) : defaults;
+        BenchmarkResult gpu;
+        float cpu_ms = 0.0f, speedup = 0.0f;
+        if (bc.compare_cpu && A->row_ptrs && (A->nnz == 0 || (A->values && A->col_indices))) {
+            const ComparisonResult cmp = compare_gpu_cpu_csr(A, x, &chosen, &bc);
+            gpu = cmp.gpu_result;
+            cpu_ms = cmp.cpu_result.avg_time_ms;
+            speedup = cmp.speedup;
+        } else {
+            gpu = benchmark_csr(A, x, &chosen, &bc);
+        }
+        const double bytes = static_cast<double>(b200::csr_compulsory_bytes(A));
+        const double peak = peak_gb_s > 0.0f ? peak_gb_s : get_gpu_peak_bandwidth();
+        const double eff = gpu.avg_time_ms > 0.0f ? bytes / 1e9 / (gpu.avg_time_ms * 1e-3) : 0.0;
+        static const char* names[] = {"SCALAR_CSR", "VECTOR_CSR", "MERGE_PATH", "ELL_KERNEL"};
+        const int k = static_cast<int>(chosen.kernel_type);
+        std::string js = benchmark_to_json(gpu);
+        js.erase(js.size() - 2);  // drop the closing "\n}" and append the roofline figures
+        char extra[640];
+        std::snprintf(extra, sizeof extra,
+                      ",\n  \"kernel\": \"%s\",\n  \"algorithmic_bytes\": %.0f,\n  \"effective_gb_s\": %.6f,\n"
+                      "  \"peak_gb_s\": %.6f,\n  \"roofline_fraction\": %.6f,\n  \"cpu_avg_time_ms\": %.6f,\n"
+                      "  \"cpu_threads\": %d,\n  \"speedup\": %.6f\n}",
+                      (k >= 0 && k < 4) ? names[k] : "SCALAR_CSR", bytes, eff, peak, peak > 0.0 ? eff / peak : 0.0,
+                      static_cast<double>(cpu_ms), cpu_ms > 0.0f ? 1 : 0, static_cast<double>(speedup));
+        js += extra;
+        if (static_cast<int>(js.size()) + 1 > cap) return 0;  // rc stays -1
+        std::memcpy(buf, js.c_str(), js.size() + 1);
+        rc = static_cast<int>(js.size());
+        return 0;
+    });
+    return status != 0 ? status : rc;
 }
 
 // ---- E. extensions ----------------------------------------------------------------------

@@ -218,12 +218,28 @@ int csr_serialize(const CSRMatrix* m, const char* filename) {
 
 // reference: src/csr_matrix.cpp:231-279.  A short file leaves the struct
 // re-shaped and reports FILE_IO, as the reference does.
+// A corrupt header must not turn into a multi-gigabyte new[] (the plain C++ API has no guard against
+// bad_alloc): a payload the file cannot hold AND larger than 1 GiB is refused before anything is
+// allocated.  Smaller short files keep the reference's behaviour -- the struct is reshaped to the
+// header, then the read fails with FILE_IO (reference src/csr_matrix.cpp:247-276).
+static bool implausible_payload(std::ifstream& f, unsigned long long payload_bytes) {
+    if (payload_bytes <= (1ull << 30)) return false;
+    const std::streampos here = f.tellg();
+    f.seekg(0, std::ios::end);
+    const std::streampos end = f.tellg();
+    f.seekg(here);
+    return !f || end < here || static_cast<unsigned long long>(end - here) < payload_bytes;
+}
+
 int csr_deserialize(CSRMatrix* m, const char* filename) {
     if (!m || !filename) return kBadArg;
     std::ifstream f(filename, std::ios::binary);
     if (!f) return kFileIo;
     int header[3] = {0, 0, 0};
     if (!read_pod(f, header, 3) || header[0] < 0 || header[1] < 0 || header[2] < 0) return kFileIo;
+    // payload announced by the header: values + col_indices + row_ptrs
+    if (implausible_payload(f, 8ull * static_cast<unsigned long long>(header[2]) + 4ull * (static_cast<unsigned long long>(header[0]) + 1)))
+        return kFileIo;
     reshape_host(m, header[0], header[1], header[2]);
     if (m->nnz > 0) {
         read_pod(f, m->values, m->nnz);
@@ -398,6 +414,8 @@ int ell_deserialize(ELLMatrix* m, const char* filename) {
     if (!f) return kFileIo;
     int header[3] = {0, 0, 0};
     if (!read_pod(f, header, 3) || header[0] < 0 || header[1] < 0 || header[2] < 0) return kFileIo;
+    if (implausible_payload(f, 8ull * static_cast<unsigned long long>(header[0]) * static_cast<unsigned long long>(header[2])))
+        return kFileIo;
     drop_host(m);
     m->num_rows = header[0];
     m->num_cols = header[1];

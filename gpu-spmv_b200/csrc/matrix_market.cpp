@@ -71,7 +71,8 @@ int csr_load_matrix_market(CSRMatrix* out, const char* filename) {
     if (rows < 0 || cols < 0 || announced < 0 || rows > 0x7fffffffll || cols > 0x7fffffffll) return bad;
 
     std::vector<Entry> entries;
-    entries.reserve(static_cast<size_t>(general ? announced : 2 * announced));
+    // the announced count comes from the file: clamp the reservation, push_back grows the vector if it was honest
+    entries.reserve(static_cast<size_t>(std::min<long long>(general ? announced : 2 * announced, 1ll << 26)));
     for (long long k = 0; k < announced; ++k) {
         long long i = 0, j = 0;
         double v = 1.0;

@@ -245,6 +245,23 @@ SPMV_B200_API int spmv_b200_benchmark_to_json(const spmv_b200_bench_result* resu
 SPMV_B200_API int spmv_b200_benchmark_from_json(const char* json,
                                                 spmv_b200_bench_result* out);    /* benchmark.h:78 */
 
+/* Roofline-aware report of the same measurement (additive; the byte format of benchmark_to_json is
+ * pinned by the reference's round-trip test, tests/test_benchmark.cu:151-170, so the extra figures
+ * get their own writer).  Runs benchmark_csr (benchmark.h:43) and, when bench_config->compare_cpu is
+ * set, times spmv_cpu_csr on the host like compare_gpu_cpu_csr (src/benchmark.cu:151-167).  The JSON
+ * object holds the reference's nine keys (same names, same formatting) followed by
+ *   "kernel"                selector decision or the caller's choice (SCALAR_CSR, ...)
+ *   "algorithmic_bytes"     8*nnz + 4*(rows+1) + 4*cols + 4*rows  (src/bandwidth.cpp:34-42)
+ *   "effective_gb_s"        algorithmic_bytes / avg_time_ms
+ *   "peak_gb_s"             peak_gb_s argument, or (<= 0) the device's theoretical HBM bandwidth
+ *   "roofline_fraction"     effective_gb_s / peak_gb_s
+ *   "cpu_avg_time_ms", "cpu_threads" (1: the reference's CPU path is single-threaded), "speedup"
+ * Returns the JSON length (excluding NUL), -1 when cap is too small, or a negative status. */
+SPMV_B200_API int spmv_b200_benchmark_csr_report(const spmv_b200_csr* A, const float* x,
+                                                 const spmv_b200_config* config,
+                                                 const spmv_b200_bench_config* bench_config,
+                                                 float peak_gb_s, char* buf, int cap);
+
 /* ======================================================================= */
 /* E. Extensions (additive; nothing in the reference corresponds)           */
 /* ======================================================================= */

@@ -92,3 +92,36 @@ for _ in range(20):
     serial()
 ms = (time.perf_counter() - t0) / 20 * 1e3
 print(f"ell host serial (H2D, spmv_ell, D2H): {ms:.3f} ms/step")
+
+# ---- floor of the host-buffer call: both PCIe directions busy at once, no compute --------------------------
+s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+for parts in (1, 8):
+    step = n // parts
+
+    def duplex():
+        for p in range(parts):
+            with torch.cuda.stream(s_up):
+                x[p * step:(p + 1) * step].copy_(xh[p * step:(p + 1) * step], non_blocking=True)
+            with torch.cuda.stream(s_down):
+                yh[p * step:(p + 1) * step].copy_(y[p * step:(p + 1) * step], non_blocking=True)
+        s_up.synchronize()
+        s_down.synchronize()
+
+    for _ in range(3):
+        duplex()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        duplex()
+    ms = (time.perf_counter() - t0) / 20 * 1e3
+    print(f"duplex copies only (67 MB up + 67 MB down at once, {parts} part(s) each): {ms:.3f} ms  "
+          f"({2 * 4 * n / ms / 1e6:.1f} GB/s both directions)")
+for name, fn in (("H2D only", lambda: x.copy_(xh, non_blocking=True)), ("D2H only", lambda: yh.copy_(y, non_blocking=True))):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        fn()
+        torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / 20 * 1e3
+    print(f"{name}: {ms:.3f} ms  ({4 * n / ms / 1e6:.1f} GB/s)")

@@ -445,3 +445,32 @@ def test_pipelined_host_buffer_ell(sp, orc, cuda):
     check(40000, 40000, rp.numpy(), ci.numpy(), va.numpy(), 8, int(np.diff(rp.numpy()).max()) <= 8, False)
     rp, ci, va = gen.random_csr(30001, 50000, 2, seed=6, device="cpu")
     check(30001, 50000, rp.numpy(), ci.numpy(), va.numpy(), 4, False, False)
+
+
+def test_benchmark_csr_report_has_roofline_fields(sp, cuda):
+    """spmv_b200_benchmark_csr_report: the reference's nine benchmark keys (src/benchmark.cu:187-202) in the
+    reference's format, followed by the roofline figures (algorithmic bytes of src/bandwidth.cpp:34-42,
+    effective GB/s, fraction of the peak) and the single-threaded CPU time next to them."""
+    import json
+    gen = gen_mod()
+    rp, ci, va = gen.random_csr(30000, 30000, 12, seed=21, device="cpu")
+    x = gen.vector_pm1(30000, 3, "cpu").numpy()
+    A = GpuCSR(sp, 30000, 30000, rp.numpy(), ci.numpy(), va.numpy())
+    buf = C.create_string_buffer(4096)
+    bc = sp.make_bench_config(2, 5, True)
+    n = sp.lib.spmv_b200_benchmark_csr_report(A.mat, x.ctypes.data_as(C.POINTER(C.c_float)), None, C.byref(bc), 6548.5, buf, 4096)
+    assert n > 0, n
+    rep = json.loads(buf.value.decode())
+    keys = list(rep)
+    assert keys[:9] == ["name", "execution_time_ms", "gflops", "bandwidth_gb_s", "avg_time_ms", "min_time_ms", "max_time_ms",
+                        "stddev_time_ms", "num_runs"]
+    assert rep["num_runs"] == 5 and rep["kernel"] in ("SCALAR_CSR", "VECTOR_CSR", "MERGE_PATH")
+    assert rep["algorithmic_bytes"] == sp.csr_bytes(30000, 30000, ci.numel())
+    assert rep["peak_gb_s"] == 6548.5 and 0.0 < rep["roofline_fraction"] < 1.5
+    assert abs(rep["effective_gb_s"] - rep["algorithmic_bytes"] / 1e9 / (rep["avg_time_ms"] * 1e-3)) <= 1e-3 * rep["effective_gb_s"]
+    assert rep["cpu_threads"] == 1 and rep["cpu_avg_time_ms"] > 0 and rep["speedup"] > 0
+    # the reference's reader still parses the object (first `"key":` wins, src/benchmark.cu:215-237)
+    back = sp.benchmark_from_json(buf.value.decode())
+    assert back.num_runs == 5
+    assert sp.lib.spmv_b200_benchmark_csr_report(A.mat, x.ctypes.data_as(C.POINTER(C.c_float)), None, C.byref(bc), 0.0, buf, 16) == -1
+    A.close()
