@@ -124,12 +124,13 @@ constexpr size_t kHotFixedSmem = static_cast<size_t>(kWorkers) * kBuf * 4 + kWor
 // the current tile is reduced.  (Two CTAs of 32 registers per SM spill and measured 1.7x slower.)
 // Measured dead ends (R-MAT 24, profiles/r1_hub_kernel.md): cold gathers through the texture pipe
 // (TLD) 5-8 % slower than LDG; L1::no_allocate gathers 3-20 % slower; two 32-register CTAs per SM
-// spill and run 1.7x slower; 128-bit stream loads (4 non-zeros per lane) 1 % slower.
-// PIPE (default): software pipeline over a worker's tiles -- while tile k is reduced, the x gathers and
-// the values of tile k+1 and the column stream (enc) of tile k+2 are already in flight, so neither the
-// DRAM latency of the stream nor the L2 latency of the gathers sits between two reduce phases.  Same
-// registers as the unpipelined form (7 values + 7 gathered x + 7 columns), same products, same order.
-template <class Row, bool ALL_HOT, bool PIPE>
+// spill and run 1.7x slower; 128-bit stream loads (4 non-zeros per lane) 1 % slower.  Round 2: a deeper software
+// pipeline (x gathers + values of tile k+1 and columns of tile k+2 issued before tile k is reduced, same
+// register count, bit-identical) made the product 12 % SLOWER (1.168 against 1.039 ms) and left the PageRank
+// step unchanged: more gathers in flight only lengthen the queue in front of the L1 miss path, which is
+// what the kernel is bound by (scripts/microbench/gather_bench.cu: L2-resident gathers retire at 1 per clock
+// and SM, L1-resident ones at 2.3, shared-memory ones at 4.4).
+template <class Row, bool ALL_HOT>
 __global__ void __launch_bounds__(kHotThreads, 1)
 merge_hot_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* __restrict__ enc,
                  const float* __restrict__ values, const float* __restrict__ x,
@@ -163,22 +164,10 @@ merge_hot_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int*
 
     int2 c0 = make_int2(0, 0), c1 = c0;
     StreamRegs cur;
-    float xv[kIPT];
     if (tile < num_tiles) {
         c0 = __ldg(coords + tile);
         c1 = __ldg(coords + tile + 1);
         load_stream(cur, c0.y, c1.y, wt, values, enc);
-        if (PIPE) {  // gathers of the first tile, columns of the second
-#pragma unroll
-            for (int u = 0; u < kIPT; ++u)
-                if (c0.y + wt + u * kT < c1.y) xv[u] = gather_one<ALL_HOT>(cur.c[u], s_hot, s_hot_addr, x);
-            if (tile + stride < num_tiles) {
-                const int2 m0 = __ldg(coords + tile + stride), m1 = __ldg(coords + tile + stride + 1);
-#pragma unroll
-                for (int u = 0; u < kIPT; ++u)
-                    if (m0.y + wt + u * kT < m1.y) cur.c[u] = dev::ld_stream_i(enc + m0.y + wt + u * kT);
-            }
-        }
     }
 
     while (tile < num_tiles) {
@@ -197,11 +186,10 @@ merge_hot_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int*
         }
 
         // ---- x gathers of this thread's share of the span (all issued before the first use) ----
-        if (!PIPE) {
+        float xv[kIPT];
 #pragma unroll
-            for (int u = 0; u < kIPT; ++u)
-                if (nz_s + wt + u * kT < nz_e) xv[u] = gather_one<ALL_HOT>(cur.c[u], s_hot, s_hot_addr, x);
-        }
+        for (int u = 0; u < kIPT; ++u)
+            if (nz_s + wt + u * kT < nz_e) xv[u] = gather_one<ALL_HOT>(cur.c[u], s_hot, s_hot_addr, x);
         // ---- row ends of the tile (tile_rows + 1 entries; the last bounds the open row) ----
         for (int i0 = wt; i0 <= tile_rows; i0 += 4 * kT) {
             int e[4];
@@ -225,27 +213,7 @@ merge_hot_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int*
             if (j < nz_e) s_prod[j - base] = cur.v[u] * xv[u];
         }
         // ---- next tile's stream: in flight while this tile is reduced ----------------------
-        if (!PIPE) {
-            if (next < num_tiles) load_stream(cur, n0.y, n1.y, wt, values, enc);
-        } else if (next < num_tiles) {
-            // tile k+1: its columns arrived during the previous reduce phase -> issue its gathers and
-            // its values now; tile k+2: issue its columns.  All of it lands while tile k is reduced.
-#pragma unroll
-            for (int u = 0; u < kIPT; ++u) {
-                const int j = n0.y + wt + u * kT;
-                if (j < n1.y) {
-                    xv[u] = gather_one<ALL_HOT>(cur.c[u], s_hot, s_hot_addr, x);
-                    cur.v[u] = dev::ld_stream_f(values + j);
-                }
-            }
-            const int next2 = next + stride;
-            if (next2 < num_tiles) {
-                const int2 m0 = __ldg(coords + next2), m1 = __ldg(coords + next2 + 1);
-#pragma unroll
-                for (int u = 0; u < kIPT; ++u)
-                    if (m0.y + wt + u * kT < m1.y) cur.c[u] = dev::ld_stream_i(enc + m0.y + wt + u * kT);
-            }
-        }
+        if (next < num_tiles) load_stream(cur, n0.y, n1.y, wt, values, enc);
         const bool first_row_split = (row_s < rows) && (nz_s > first_row_start);
         worker_sync(w);
 
@@ -453,13 +421,13 @@ int device_sms() {
     return sms;
 }
 
-template <class Row, bool ALL_HOT, bool PIPE>
+template <class Row, bool ALL_HOT>
 cudaError_t run_hot_variant(const CsrView& A, const HotPlan& hot, const float* x, const MergePlan& plan,
                             const Row& row_op, cudaStream_t stream, int* grid_out) {
     const int sms = device_sms();
     const int n_hot = ALL_HOT ? A.cols : hot.n_hot;
     const size_t smem = static_cast<size_t>((n_hot + 3) & ~3) * 4 + kHotFixedSmem;
-    auto kernel = merge_hot_kernel<Row, ALL_HOT, PIPE>;
+    auto kernel = merge_hot_kernel<Row, ALL_HOT>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     int grid = sms;  // persistent: one CTA per SM
@@ -476,13 +444,8 @@ cudaError_t run_hot_variant(const CsrView& A, const HotPlan& hot, const float* x
 template <class Row>
 cudaError_t run_hot(const CsrView& A, const HotPlan& hot, const float* x, const MergePlan& plan, const Row& row_op,
                     cudaStream_t stream, int* grid_out) {
-    static const int pipe = hot_env_int("SPMV_B200_HOT_PIPE", 1);  // 0: the unpipelined form (A/B timing)
-    if (hot.all_hot) {
-        return pipe ? run_hot_variant<Row, true, true>(A, hot, x, plan, row_op, stream, grid_out)
-                    : run_hot_variant<Row, true, false>(A, hot, x, plan, row_op, stream, grid_out);
-    }
-    return pipe ? run_hot_variant<Row, false, true>(A, hot, x, plan, row_op, stream, grid_out)
-                : run_hot_variant<Row, false, false>(A, hot, x, plan, row_op, stream, grid_out);
+    if (hot.all_hot) return run_hot_variant<Row, true>(A, hot, x, plan, row_op, stream, grid_out);
+    return run_hot_variant<Row, false>(A, hot, x, plan, row_op, stream, grid_out);
 }
 
 }  // namespace

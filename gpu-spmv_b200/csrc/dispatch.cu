@@ -17,6 +17,8 @@
 // re-walking the host arrays after every call.
 #include "internal.hpp"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
@@ -25,6 +27,10 @@
 
 namespace spmv {
 namespace b200 {
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
+
 
 // ---- launch accounting ----------------------------------------------------------
 static std::atomic<unsigned long long> g_launches{0};
@@ -144,6 +150,7 @@ cudaError_t planned_build(const CsrView& A, PlannedCsr* out, int capacity, bool 
 }
 
 int csr_plan_create(const CSRMatrix* A, int max_hot_columns, int flags, CsrPlan** out) {
+    NvtxRange nvtx_range("spmv_b200:csr_plan_create");
     const bool force = (flags & kPlanForce) != 0;
     if (!A || !out) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     if (!A->d_row_ptrs || !A->d_col_indices || (A->nnz > 0 && !A->d_values))
@@ -213,6 +220,7 @@ void csr_plan_info(const CsrPlan* p, int* hot_columns, long long* hot_nnz, int* 
 }
 
 int spmv_csr_planned(const CsrPlan* p, const float* d_x, float* d_y, cudaStream_t stream) {
+    NvtxRange nvtx_range("spmv_b200:spmv_csr_planned");
     if (!p || !d_x || !d_y) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     const CsrView& A = p->A;
     if (A.rows <= 0) return 0;
@@ -419,6 +427,7 @@ int spmv_ell_async(const ELLMatrix* A, const float* d_x, float* d_y, cudaStream_
 
 // ------------------------------------------------------------------- spmv_csr --
 SpMVResult spmv_csr(const CSRMatrix* A, const float* d_x, float* d_y, const SpMVConfig* config, int vec_size) {
+    b200::NvtxRange nvtx_range("spmv_b200:spmv_csr");
     if (!A || !d_x || !d_y) return b200::failed(SpMVError::INVALID_ARGUMENT);
     if (vec_size >= 0 && !spmv_validate_dimensions(A->num_cols, vec_size))
         return b200::failed(SpMVError::INVALID_DIMENSION);
@@ -451,6 +460,7 @@ SpMVResult spmv_csr(const CSRMatrix* A, const float* d_x, float* d_y, const SpMV
 
 // ------------------------------------------------------------------- spmv_ell --
 SpMVResult spmv_ell(const ELLMatrix* A, const float* d_x, float* d_y, const SpMVConfig* /*config*/, int vec_size) {
+    b200::NvtxRange nvtx_range("spmv_b200:spmv_ell");
     if (!A || !d_x || !d_y) return b200::failed(SpMVError::INVALID_ARGUMENT);
     if (vec_size >= 0 && !spmv_validate_dimensions(A->num_cols, vec_size))
         return b200::failed(SpMVError::INVALID_DIMENSION);

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -87,7 +88,12 @@ int ell_host_plan_create(const ELLMatrix* A, int chunks, EllHostPlan** out) {
     auto round_up = [](long long v, long long m) { return (v + m - 1) / m * m; };
     p->chunk_rows = static_cast<int>(std::max<long long>(1024, round_up((static_cast<long long>(p->rows) + chunks - 1) / chunks, 1024)));
     p->chunks = p->rows > 0 ? (p->rows + p->chunk_rows - 1) / p->chunk_rows : 0;
-    p->x_chunk = static_cast<int>(std::max<long long>(1024, round_up((static_cast<long long>(p->cols) + chunks - 1) / chunks, 1024)));
+    // x travels in chunks of the same size as the rows.  (Measured: finer x chunks -- 4 or 8 per row chunk, so that
+    // a banded row chunk waits for less beyond its own rows -- cost more in per-copy overhead than they gain:
+    // 2.09 / 2.31 ms against 1.83 ms; SPMV_B200_HOST_X_SPLIT keeps the experiment reproducible.)
+    static const int x_per_row_chunk = [] { const char* v = getenv("SPMV_B200_HOST_X_SPLIT"); const int k = v ? atoi(v) : 1; return k < 1 ? 1 : (k > 16 ? 16 : k); }();
+    const long long xc = static_cast<long long>(chunks) * x_per_row_chunk;
+    p->x_chunk = static_cast<int>(std::max<long long>(1024, round_up((static_cast<long long>(p->cols) + xc - 1) / xc, 1024)));
     p->x_chunks = p->cols > 0 ? (p->cols + p->x_chunk - 1) / p->x_chunk : 0;
     bool ok = cudaMalloc(&p->d_x, sizeof(float) * static_cast<size_t>(std::max(p->cols, 1))) == cudaSuccess &&
               cudaMalloc(&p->d_y, sizeof(float) * static_cast<size_t>(std::max(p->rows, 1))) == cudaSuccess &&
@@ -134,6 +140,7 @@ void ell_host_plan_destroy(EllHostPlan* p) { delete p; }
 // Blocking: returns when y_host is complete.  x_host / y_host should be page-locked (cudaHostAlloc /
 // cudaHostRegister) for the copies to overlap; pageable memory works but serialises.
 int spmv_ell_host(EllHostPlan* p, const float* x_host, float* y_host) {
+    NvtxRange nvtx_range("spmv_b200:spmv_ell_host");
     if (!p || !x_host || !y_host) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     if (p->rows <= 0) return 0;
     bool ok = true;
@@ -153,6 +160,18 @@ int spmv_ell_host(EllHostPlan* p, const float* x_host, float* y_host) {
         ok = ok && cudaMemcpyAsync(y_host, p->d_y, sizeof(float) * static_cast<size_t>(p->rows), cudaMemcpyDeviceToHost, p->s_run) == cudaSuccess;
         ok = ok && cudaStreamSynchronize(p->s_run) == cudaSuccess;
     } else if (ok) {
+        // y in page-locked, device-mapped host memory (cudaHostAlloc / cudaHostRegister: what a pinned buffer is
+        // under UVA): the kernel stores its rows STRAIGHT into y_host over PCIe -- the download is the kernel's
+        // own posted writes, overlapped row by row with the product, no staging buffer, no per-chunk copy.
+        float* y_direct = nullptr;
+        static const int zero_copy = [] { const char* v = getenv("SPMV_B200_HOST_ZERO_COPY_Y"); return v ? atoi(v) : 1; }();
+        if (zero_copy) {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, y_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+                y_direct = static_cast<float*>(attr.devicePointer);
+            else
+                cudaGetLastError();
+        }
         int waited = -1;  // highest x chunk the compute stream already waits for
         for (int c = 0; ok && c < p->chunks; ++c) {
             const int lo = c * p->chunk_rows, hi = std::min(p->rows, lo + p->chunk_rows);
@@ -160,13 +179,14 @@ int spmv_ell_host(EllHostPlan* p, const float* x_host, float* y_host) {
                 ok = cudaStreamWaitEvent(p->s_run, p->ev_x[p->need[c]], 0) == cudaSuccess;
                 waited = p->need[c];
             }
-            ok = ok && launch_ell_rows(p->rows, p->width, p->d_cols, p->d_vals, p->d_x, p->d_y, lo, hi, p->s_run) == cudaSuccess;
+            ok = ok && launch_ell_rows(p->rows, p->width, p->d_cols, p->d_vals, p->d_x, y_direct ? y_direct : p->d_y, lo, hi, p->s_run) == cudaSuccess;
+            if (y_direct) continue;
             ok = ok && cudaEventRecord(p->ev_y[c], p->s_run) == cudaSuccess;
             ok = ok && cudaStreamWaitEvent(p->s_down, p->ev_y[c], 0) == cudaSuccess;
             ok = ok && cudaMemcpyAsync(y_host + lo, p->d_y + lo, sizeof(float) * static_cast<size_t>(hi - lo),
                                        cudaMemcpyDeviceToHost, p->s_down) == cudaSuccess;
         }
-        ok = ok && cudaStreamSynchronize(p->s_down) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(y_direct ? p->s_run : p->s_down) == cudaSuccess;
         ok = cudaStreamSynchronize(p->s_up) == cudaSuccess && ok;  // x chunks no row read (none for a square matrix)
     }
     if (!ok) {

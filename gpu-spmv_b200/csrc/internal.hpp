@@ -22,6 +22,18 @@ SpMVConfig reference_policy(const CSRMatrix* A);
 size_t csr_compulsory_bytes(const CSRMatrix* A);
 size_t ell_compulsory_bytes(const ELLMatrix* A);
 
+// ---- NVTX ranges (the reference has none; SURVEY 5 "tracing") ----------------------
+// Header-only NVTX v3: a no-op costing one indirect call unless a tool (nsys, ncu --nvtx) is attached.
+// Ranges: spmv_b200:spmv_csr / spmv_ell / spmv_csr_planned / csr_plan_create / spmv_ell_host /
+// pagerank_device / pagerank_multi.run -- `ncu --nvtx --nvtx-include "spmv_b200:pagerank_device/"` profiles
+// exactly the kernels of one entry point (scripts/ncu_capture.sh).
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 // ---- launch accounting ----------------------------------------------------------
 void count_launches(int n);
 unsigned long long launch_count();

@@ -156,6 +156,7 @@ double* pr_plan_tmp(PrPlan* p) { return p->tmp; }
 int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,
                     float* final_residual, bool* converged, double* l1_residual, bool normalize, float* l2_history,
                     int history_capacity) {
+    NvtxRange nvtx_range("spmv_b200:pagerank_device");
     if (!adj || !d_ranks) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     PageRankConfig defaults;
     if (!config) config = &defaults;

@@ -529,6 +529,7 @@ bool wait_history(PrDist* d, int iteration /* 1-based */, double timeout_s) {
 }  // namespace
 
 int pr_dist_run(PrDist* d, const PageRankConfig* config, int fixed_iterations, PrDistResult* out) {
+    NvtxRange nvtx_range("spmv_b200:pagerank_multi.run");
     if (!d || !out) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     PageRankConfig defaults;
     if (!config) config = &defaults;

@@ -49,8 +49,8 @@ def main():
         rp, ci, va = gen.short_rows_with_outliers_csr(n, 43, dev)
         bounds = [0, n]
     else:
-        n, bounds, rp, ci, va, n_edges = B.build_rmat_shard(torch, gen, args.scale, 16, args.seed, 0, 1, dev,
-                                                            relabelled=args.relabelled)
+        n, bounds, rp, ci, va, n_edges = gen.rmat_pagerank_shard(args.scale, 16, args.seed, 0, 1, dev,
+                                                                 relabelled=args.relabelled)
     torch.cuda.synchronize()
     A = sp.DeviceCSR(n, n, rp, ci, va)
     x = gen.vector_pm1(n, 7, dev)

@@ -62,7 +62,7 @@ yh = torch.empty(n).pin_memory()
 res = sp.SpMVResult()
 assert sp.lib.spmv_b200_spmv_ell(E, sp.dptr(x), sp.dptr(y), None, n, C.byref(res)) == 0
 y_ref = y.cpu()
-for chunks in (4, 8, 16, 32, 64):
+for chunks in (6, 8, 12, 16, 24, 32):
     plan = C.c_void_p()
     assert sp.lib.spmv_b200_ell_host_plan_create(E, chunks, C.byref(plan)) == 0
     for _ in range(3):
