@@ -247,6 +247,21 @@ def ncu_traffic_for(kernel_name):
         return None, f"unavailable ({type(exc).__name__})"
 
 
+def nvlink_bytes(index):
+    """(tx, rx) data bytes moved over all NVLinks of GPU `index` so far (`nvidia-smi nvlink -gt d`), or None."""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True,
+                             timeout=20).stdout
+    except Exception:
+        return None
+    tx = sum(int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+    rx = sum(int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+    if not re.search(r"Data Tx", out):
+        return None
+    return tx * 1024, rx * 1024
+
+
 def vector_checksum(torch, v):
     """Two 64-bit integer checksums of the bit pattern of a float32 device vector (order-sensitive)."""
     bits = v.view(torch.int32).to(torch.int64)
@@ -270,6 +285,7 @@ def run_product_arm(args):
     dist_on = world > 1
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     sp = load_pkg()
     import gpu_spmv_b200.dist as D
@@ -359,6 +375,8 @@ def run_product_arm(args):
 
     host_plan = C.c_void_p()
     assert sp.lib.spmv_b200_ell_host_plan_create(E, 0, C.byref(host_plan)) == 0
+    h2d_bytes, d2h_bytes = C.c_ulonglong(0), C.c_ulonglong(0)
+    assert sp.lib.spmv_b200_ell_host_plan_bytes(host_plan, C.byref(h2d_bytes), C.byref(d2h_bytes)) == 0
 
     def e2e_step():  # blocking: returns when y_host is complete
         rc = sp.lib.spmv_b200_spmv_ell_host(host_plan, x_host.data_ptr(), y_host.data_ptr())
@@ -382,8 +400,8 @@ def run_product_arm(args):
     e2e_same = bool(torch.equal(y_host.view(torch.int32), y_device_path.cpu().view(torch.int32)))
     serial_sec = wall_time(e2e_serial_step, e2e_steps)
     sp.lib.spmv_b200_ell_host_plan_destroy(host_plan)
-    e2e = {"value": world * ell_bytes / e2e_sec / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * n_cols,
-           "d2h_bytes_per_step": 4 * n_loc, "ms_per_step": e2e_sec * 1e3,
+    e2e = {"value": world * ell_bytes / e2e_sec / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d_bytes.value) * world,
+           "d2h_bytes_per_step": int(d2h_bytes.value) * world, "ms_per_step": e2e_sec * 1e3,
            "api": "spmv_b200_spmv_ell_host (blocking C ABI, pinned host x -> pinned host y; H2D / kernel / D2H "
                   "pipelined over row chunks on three streams)",
            "bit_identical_to_device_path": e2e_same,
@@ -568,10 +586,14 @@ def run_product_arm(args):
             pr = D.NativeShardedPageRank(c, csr, bounds[rank], n, names[mode])
             used = D.EXCHANGE_NAMES[pr.exchange] if dist_on else "none (1 GPU)"
             sec = None
-            for _ in range(2):  # the first run also builds the dangling set and captures the CUDA graphs
+            link0 = None
+            for rep in range(2):  # the first run also builds the dangling set and captures the CUDA graphs
+                if rep == 1 and dist_on:
+                    link0 = nvlink_bytes(local_rank)
                 res = pr.run(0.85, 0.0, 0, fixed_iterations=iters)
                 t = max_over_ranks(res.device_seconds)
                 sec = t if sec is None else min(sec, t)
+            link1 = nvlink_bytes(local_rank) if link0 is not None else None
             vec = pr.ranks(dev)
             total = float(vec.double().sum().item())
             checks[mode] = vector_checksum(torch, vec) + (total,)
@@ -584,6 +606,15 @@ def run_product_arm(args):
                      "rows_per_rank_max": int(max(bounds[i + 1] - bounds[i] for i in range(world))),
                      "timing": "CUDA events around the whole loop on every rank (inside spmv_b200_pr_dist_run), max over ranks; "
                                "excluded: set-up and the final normalisation"}
+            if dist_on:
+                # NVLink data counters of this rank's GPU around the timed run (driver counters, not a profiler):
+                # egress / ingress per iteration, max over ranks -- the evidence for "multicast sends every row once"
+                have = link0 is not None and link1 is not None
+                tx = max_over_ranks((link1[0] - link0[0]) / res.iterations_launched if have else -1.0)
+                rx = max_over_ranks((link1[1] - link0[1]) / res.iterations_launched if have else -1.0)
+                entry["nvlink_tx_mb_per_iter_max_rank"] = r4(tx / 1e6) if tx >= 0 else None
+                entry["nvlink_rx_mb_per_iter_max_rank"] = r4(rx / 1e6) if rx >= 0 else None
+                entry["slice_bytes_max_rank"] = int(max(bounds[i + 1] - bounds[i] for i in range(world))) * 4
             extra[f"pagerank{tag}_{mode}" if dist_on else f"pagerank{tag}"] = entry
             if best is None or entry["iters_per_s"] > best[1]["iters_per_s"]:
                 best = (mode, entry)

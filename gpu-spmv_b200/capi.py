@@ -137,6 +137,8 @@ PROTOTYPES = {
     "spmv_b200_benchmark_csr_report": (C.c_int, [CSR_P, c_float_p, CFG_P, BC_P, C.c_float, C.c_char_p, C.c_int]),
     # E. extensions
     "spmv_b200_version": (C.c_char_p, []),
+    "spmv_b200_set_l2_fetch_granularity": (C.c_int, [C.c_int]),
+    "spmv_b200_get_l2_fetch_granularity": (C.c_int, []),
     "spmv_b200_launch_count": (C.c_ulonglong, []),
     "spmv_b200_reference_policy": (C.c_int, [CSR_P, CFG_P]),
     "spmv_b200_spmv_csr_async": (C.c_int, [CSR_P, vp, vp, CFG_P, vp]),
@@ -158,6 +160,7 @@ PROTOTYPES = {
     "spmv_b200_ell_host_plan_destroy": (None, [vp]),
     "spmv_b200_spmv_ell_host": (C.c_int, [vp, vp, vp]),
     "spmv_b200_ell_host_plan_info": (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
+    "spmv_b200_ell_host_plan_bytes": (C.c_int, [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "spmv_b200_ell_from_csr_device": (C.c_int, [ELL_P, CSR_P]),
     "spmv_b200_merge_path_search": (C.c_int, [C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p]),
     "spmv_b200_partition_rows": (C.c_int, [c_int_p, C.c_int, C.c_int, c_int_p]),

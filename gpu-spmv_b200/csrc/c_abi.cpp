@@ -213,6 +213,12 @@ int spmv_b200_ell_host_plan_info(const spmv_b200_ell_host_plan* plan, int* chunk
     return 0;
 }
 
+int spmv_b200_ell_host_plan_bytes(const spmv_b200_ell_host_plan* plan, unsigned long long* h2d, unsigned long long* d2h) {
+    if (!plan) return kBadArg;
+    b200::ell_host_plan_bytes(reinterpret_cast<const b200::EllHostPlan*>(plan), h2d, d2h);
+    return 0;
+}
+
 // ---- D. bandwidth / PageRank / benchmark ------------------------------------------------
 int spmv_b200_bandwidth_csr(const spmv_b200_csr* A, float ms, spmv_b200_bandwidth* out) {
     if (!out) return kBadArg;
@@ -335,6 +341,23 @@ int spmv_b200_benchmark_csr_report(const spmv_b200_csr* A_c, const float* x, con
         return 0;
     });
     return status != 0 ? status : rc;
+}
+
+int spmv_b200_set_l2_fetch_granularity(int bytes) {
+    if (bytes != 32 && bytes != 64 && bytes != 128) return kBadArg;
+    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(bytes)) != cudaSuccess) {
+        cudaGetLastError();
+        return SPMV_B200_KERNEL_LAUNCH;
+    }
+    return 0;
+}
+int spmv_b200_get_l2_fetch_granularity(void) {
+    size_t v = 0;
+    if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) != cudaSuccess) {
+        cudaGetLastError();
+        return SPMV_B200_KERNEL_LAUNCH;
+    }
+    return static_cast<int>(v);
 }
 
 // ---- E. extensions ----------------------------------------------------------------------

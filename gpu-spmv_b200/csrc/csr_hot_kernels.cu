@@ -59,6 +59,23 @@ __device__ __forceinline__ void worker_sync(int w) {
 
 // x entry of an encoded column: e < 0 -> slot ~e of the shared-memory table, else x[e].
 // Predicated, not branched: a lane that reads the table issues no L1 wavefront.
+__device__ __forceinline__ float gather_enc_hint(int e, uint32_t s_hot_addr, const float* __restrict__ x, uint64_t policy) {
+    float r;
+    const uint32_t sa = s_hot_addr + (static_cast<uint32_t>(~e) << 2);
+    const unsigned long long ga = reinterpret_cast<unsigned long long>(x) +
+                                  static_cast<unsigned long long>(static_cast<long long>(e) * 4);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.lt.s32 p, %1, 0;\n"
+        "@p ld.shared.f32 %0, [%2];\n"
+        "@!p ld.global.nc.L2::cache_hint.f32 %0, [%3], %4;\n"
+        "}\n"
+        : "=f"(r)
+        : "r"(e), "r"(sa), "l"(ga), "l"(policy));
+    return r;
+}
+
 __device__ __forceinline__ float gather_enc(int e, uint32_t s_hot_addr, const float* __restrict__ x) {
     float r;
     const uint32_t sa = s_hot_addr + (static_cast<uint32_t>(~e) << 2);
@@ -83,8 +100,21 @@ struct StreamRegs {
     int c[kIPT];
 };
 
+// l2_mode bit 0: the stream is loaded with L2::evict_first (read once; must not displace x in L2)
 __device__ __forceinline__ void load_stream(StreamRegs& s, int nz_s, int nz_e, int wt,
-                                            const float* __restrict__ values, const int* __restrict__ enc) {
+                                            const float* __restrict__ values, const int* __restrict__ enc,
+                                            unsigned l2_mode, uint64_t pol_first) {
+    if (l2_mode & 1u) {
+#pragma unroll
+        for (int u = 0; u < kIPT; ++u) {
+            const int j = nz_s + wt + u * kT;
+            if (j < nz_e) {
+                s.v[u] = dev::ld_stream_f_hint(values + j, pol_first);
+                s.c[u] = dev::ld_stream_i_hint(enc + j, pol_first);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int u = 0; u < kIPT; ++u) {
         const int j = nz_s + wt + u * kT;
@@ -95,10 +125,12 @@ __device__ __forceinline__ void load_stream(StreamRegs& s, int nz_s, int nz_e, i
     }
 }
 
+// l2_mode bit 1: cold gathers carry L2::evict_last (x is what should stay in L2)
 template <bool ALL_HOT>
 __device__ __forceinline__ float gather_one(int e, const float* s_hot, uint32_t s_hot_addr,
-                                            const float* __restrict__ x) {
+                                            const float* __restrict__ x, unsigned l2_mode, uint64_t pol_last) {
     if (ALL_HOT) return s_hot[e];
+    if (l2_mode & 2u) return gather_enc_hint(e, s_hot_addr, x, pol_last);
     return gather_enc(e, s_hot_addr, x);
 }
 
@@ -136,8 +168,10 @@ merge_hot_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int*
                  const float* __restrict__ values, const float* __restrict__ x,
                  const int* __restrict__ hot_cols, int n_hot, const int2* __restrict__ coords, int num_tiles,
                  int* __restrict__ carry_row, float* __restrict__ carry_val, Row row_op,
-                 double* __restrict__ partials) {
+                 double* __restrict__ partials, unsigned l2_mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint64_t pol_first = dev::l2_policy_evict_first();
+    const uint64_t pol_last = dev::l2_policy_evict_last();
     const int hot_slots = (n_hot + 3) & ~3;
     float* s_hot = reinterpret_cast<float*>(smem_raw);
     const int tid = threadIdx.x;
@@ -167,7 +201,7 @@ merge_hot_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int*
     if (tile < num_tiles) {
         c0 = __ldg(coords + tile);
         c1 = __ldg(coords + tile + 1);
-        load_stream(cur, c0.y, c1.y, wt, values, enc);
+        load_stream(cur, c0.y, c1.y, wt, values, enc, l2_mode, pol_first);
     }
 
     while (tile < num_tiles) {
@@ -189,7 +223,7 @@ merge_hot_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int*
         float xv[kIPT];
 #pragma unroll
         for (int u = 0; u < kIPT; ++u)
-            if (nz_s + wt + u * kT < nz_e) xv[u] = gather_one<ALL_HOT>(cur.c[u], s_hot, s_hot_addr, x);
+            if (nz_s + wt + u * kT < nz_e) xv[u] = gather_one<ALL_HOT>(cur.c[u], s_hot, s_hot_addr, x, l2_mode, pol_last);
         // ---- row ends of the tile (tile_rows + 1 entries; the last bounds the open row) ----
         for (int i0 = wt; i0 <= tile_rows; i0 += 4 * kT) {
             int e[4];
@@ -213,7 +247,7 @@ merge_hot_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int*
             if (j < nz_e) s_prod[j - base] = cur.v[u] * xv[u];
         }
         // ---- next tile's stream: in flight while this tile is reduced ----------------------
-        if (next < num_tiles) load_stream(cur, n0.y, n1.y, wt, values, enc);
+        if (next < num_tiles) load_stream(cur, n0.y, n1.y, wt, values, enc, l2_mode, pol_first);
         const bool first_row_split = (row_s < rows) && (nz_s > first_row_start);
         worker_sync(w);
 
@@ -430,13 +464,18 @@ cudaError_t run_hot_variant(const CsrView& A, const HotPlan& hot, const float* x
     auto kernel = merge_hot_kernel<Row, ALL_HOT>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
+    // L2 priorities (bit 0: stream evict_first, bit 1: x gathers evict_last).  Default: on when x does not
+    // fit L2 comfortably (> 64 MB), where the 8 B/nnz stream would otherwise push x out; SPMV_B200_HOT_L2 forces.
+    static const int env_l2 = hot_env_int("SPMV_B200_HOT_L2", -1);
+    const int l2_mode = env_l2 >= 0 ? env_l2 : 0;
     int grid = sms;  // persistent: one CTA per SM
     if (grid > plan.num_tiles / kWorkers) grid = plan.num_tiles / kWorkers;  // per-worker sums fit plan.partials
     if (grid < 1) grid = 1;
     if (grid_out) *grid_out = grid;
     kernel<<<grid, kHotThreads, smem, stream>>>(A.rows, A.nnz, A.row_ptrs, ALL_HOT ? A.col_indices : hot.enc, A.values, x,
                                                 ALL_HOT ? nullptr : hot.hot_cols, n_hot, plan.coords, plan.num_tiles,
-                                                plan.carry_row, plan.carry_val, row_op, plan.partials);
+                                                plan.carry_row, plan.carry_val, row_op, plan.partials,
+                                                static_cast<unsigned>(l2_mode));
     count_launches(1);
     return cudaGetLastError();
 }

@@ -50,6 +50,29 @@ __device__ __forceinline__ int ld_stream_i(const int* p) {
     return r;
 }
 
+// ---- L2 eviction-priority hints (createpolicy + ld ... .L2::cache_hint) ---------
+// The matrix stream is read once: evict_first keeps it from pushing the re-used x entries out of L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float ld_stream_f_hint(const float* p, uint64_t policy) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ int ld_stream_i_hint(const int* p, uint64_t policy) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy));
+    return r;
+}
+
 // ---- gathers of x (re-used: read-only path, L1-allocating) -----------------
 
 __device__ __forceinline__ float ld_x(const float* p) {

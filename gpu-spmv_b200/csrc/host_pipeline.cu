@@ -58,6 +58,8 @@ struct EllHostPlan {
     int chunks = 0, chunk_rows = 0;   // row chunks
     int x_chunks = 0, x_chunk = 0;    // x chunks (entries)
     std::vector<int> need;            // last x chunk a row chunk reads (-1: none)
+    std::vector<char> x_needed;       // x chunks some row reads: the others are never uploaded (a row shard of a
+                                      // larger system reads only its own band of x)
     bool ranged = false;              // the row-range kernel applies; else one launch after all of x
     float* d_x = nullptr;
     float* d_y = nullptr;
@@ -106,6 +108,7 @@ int ell_host_plan_create(const ELLMatrix* A, int chunks, EllHostPlan** out) {
     for (auto& e : p->ev_x) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     for (auto& e : p->ev_y) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     p->need.assign(p->chunks, p->x_chunks - 1);
+    p->x_needed.assign(p->x_chunks, 1);
     // does the row-range kernel apply to this matrix?  (same test as launch_ell_rows)
     p->ranged = p->width >= 1 && p->width <= 8 && p->rows % 4 == 0 &&
                 ((reinterpret_cast<uintptr_t>(p->d_cols) | reinterpret_cast<uintptr_t>(p->d_vals)) & 15u) == 0;
@@ -122,6 +125,14 @@ int ell_host_plan_create(const ELLMatrix* A, int chunks, EllHostPlan** out) {
                  cudaMemcpy(h_max.data(), d_max, sizeof(int) * p->chunks, cudaMemcpyDeviceToHost) == cudaSuccess;
             // x chunks are uploaded in index order on one stream, so "the last chunk read" is what a row chunk waits for
             for (int c = 0; ok && c < p->chunks; ++c) p->need[c] = h_max[c] < 0 ? -1 : std::min(h_max[c], p->cols - 1) / p->x_chunk;
+            if (ok) {
+                p->x_needed.assign(p->x_chunks, 0);
+                for (int c = 0; c < p->chunks; ++c) {
+                    if (h_max[c] < 0) continue;
+                    const int lo = std::max(h_min[c], 0) / p->x_chunk, hi = p->need[c];
+                    for (int j = lo; j <= hi; ++j) p->x_needed[j] = 1;
+                }
+            }
         }
         cudaFree(d_min);
         cudaFree(d_max);
@@ -149,6 +160,7 @@ int spmv_ell_host(EllHostPlan* p, const float* x_host, float* y_host) {
     ok = ok && cudaStreamWaitEvent(p->s_up, p->ev_start, 0) == cudaSuccess;
     ok = ok && cudaStreamWaitEvent(p->s_run, p->ev_start, 0) == cudaSuccess;
     for (int j = 0; ok && j < p->x_chunks; ++j) {
+        if (!p->x_needed[j]) continue;
         const size_t lo = static_cast<size_t>(j) * p->x_chunk;
         const size_t n = std::min<size_t>(p->x_chunk, static_cast<size_t>(p->cols) - lo);
         ok = cudaMemcpyAsync(p->d_x + lo, x_host + lo, n * sizeof(float), cudaMemcpyHostToDevice, p->s_up) == cudaSuccess &&
@@ -196,6 +208,20 @@ int spmv_ell_host(EllHostPlan* p, const float* x_host, float* y_host) {
         return static_cast<int>(SpMVError::KERNEL_LAUNCH);
     }
     return 0;
+}
+
+// bytes one call moves over PCIe: the x chunks some row reads, and y
+void ell_host_plan_bytes(const EllHostPlan* p, unsigned long long* h2d, unsigned long long* d2h) {
+    unsigned long long up = 0;
+    if (p) {
+        for (int j = 0; j < p->x_chunks; ++j) {
+            if (!p->x_needed[j]) continue;
+            const size_t lo = static_cast<size_t>(j) * p->x_chunk;
+            up += sizeof(float) * std::min<size_t>(p->x_chunk, static_cast<size_t>(p->cols) - lo);
+        }
+    }
+    if (h2d) *h2d = up;
+    if (d2h) *d2h = p ? sizeof(float) * static_cast<unsigned long long>(p->rows) : 0;
 }
 
 void ell_host_plan_info(const EllHostPlan* p, int* chunks, int* ranged, int* max_lookahead) {

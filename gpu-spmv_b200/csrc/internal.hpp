@@ -285,6 +285,7 @@ int ell_host_plan_create(const ELLMatrix* A, int chunks, EllHostPlan** out);
 void ell_host_plan_destroy(EllHostPlan* plan);
 int spmv_ell_host(EllHostPlan* plan, const float* x_host, float* y_host);
 void ell_host_plan_info(const EllHostPlan* plan, int* chunks, int* ranged, int* max_lookahead);
+void ell_host_plan_bytes(const EllHostPlan* plan, unsigned long long* h2d, unsigned long long* d2h);
 
 // ---- PageRank plan over one row shard (pagerank.cu) -------------------------------------
 struct PrPlan;

@@ -267,6 +267,12 @@ SPMV_B200_API int spmv_b200_benchmark_csr_report(const spmv_b200_csr* A, const f
 /* ======================================================================= */
 
 SPMV_B200_API const char* spmv_b200_version(void);
+/* cudaLimitMaxL2FetchGranularity of the current device (32, 64 or 128 bytes; a hint the driver may
+ * round): a product whose x does not fit L2 (config 3: 200 MB of x behind random columns) pays DRAM for
+ * every gather, and at the default granularity each 4-byte gather fetches 64 bytes.  get returns the
+ * current value or a negative status. */
+SPMV_B200_API int spmv_b200_set_l2_fetch_granularity(int bytes);
+SPMV_B200_API int spmv_b200_get_l2_fetch_granularity(void);
 /* number of kernels this library has launched in this process so far */
 SPMV_B200_API unsigned long long spmv_b200_launch_count(void);
 /* the reference's selector decision without the B200 outlier override
@@ -300,6 +306,10 @@ SPMV_B200_API int spmv_b200_spmv_ell_host(spmv_b200_ell_host_plan* plan, const f
  * own index any row chunk has to wait for (0-1 for a banded matrix, chunks - 1 in the worst case) */
 SPMV_B200_API int spmv_b200_ell_host_plan_info(const spmv_b200_ell_host_plan* plan, int* chunks,
                                                int* ranged, int* max_lookahead);
+/* bytes one call moves over PCIe: only the x chunks some row of the matrix reads are uploaded (a row
+ * shard of a larger system reads its own band of x), plus all of y */
+SPMV_B200_API int spmv_b200_ell_host_plan_bytes(const spmv_b200_ell_host_plan* plan,
+                                                unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
 
 /* device-side ELL assembly from the DEVICE arrays of csr (ell_from_csr
  * semantics, src/ell_matrix.cpp:111-159); fills ell's device arrays only
