@@ -248,8 +248,26 @@ def ncu_traffic_for(kernel_name):
 
 
 def nvlink_bytes(index):
-    """(tx, rx) data bytes moved over all NVLinks of GPU `index` so far (`nvidia-smi nvlink -gt d`), or None."""
+    """(tx, rx) payload bytes moved over all NVLinks of GPU `index` so far, or None when the driver does not
+    count them: NVML field values NVLINK_THROUGHPUT_DATA_TX / _RX summed over the links (KiB units), else
+    `nvidia-smi nvlink -gt d`."""
     import re
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        tx_id = getattr(pynvml, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138)
+        rx_id = getattr(pynvml, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX", 139)
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(tx_id, 0xFFFFFFFF), (rx_id, 0xFFFFFFFF)])  # scope: all links
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                raise RuntimeError("field not supported")
+            out.append(int(v.value.ullVal) * 1024)
+        if out[0] or out[1]:
+            return out[0], out[1]
+    except Exception:
+        pass
     try:
         out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True,
                              timeout=20).stdout
@@ -257,8 +275,8 @@ def nvlink_bytes(index):
         return None
     tx = sum(int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
     rx = sum(int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
-    if not re.search(r"Data Tx", out):
-        return None
+    if not re.search(r"Data Tx", out) or (tx == 0 and rx == 0):
+        return None  # counters absent or not maintained on this box
     return tx * 1024, rx * 1024
 
 
@@ -280,6 +298,11 @@ def run_product_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    # stdout carries exactly ONE JSON line: whatever libraries print while the benchmark runs (NCCL writes its
+    # version banner with printf) goes to stderr; the real stdout is restored for the line at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist_on = world > 1
@@ -708,7 +731,10 @@ def run_product_arm(args):
         }
         line.update(scalars)
         line["extra"] = extra
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if comm is not None:
         comm.close()
     if dist_on:

@@ -85,7 +85,7 @@ int ell_host_plan_create(const ELLMatrix* A, int chunks, EllHostPlan** out) {
     if (!p) return static_cast<int>(SpMVError::OUT_OF_MEMORY);
     p->rows = A->num_rows; p->cols = A->num_cols; p->width = A->max_nnz_per_row;
     p->d_cols = A->d_col_indices; p->d_vals = A->d_values;
-    if (chunks <= 0) chunks = 8;  // measured on B200 / PCIe Gen5 (config 2): 4 / 8 / 16 / 32 chunks -> 2.02 / 1.85 / 1.89 / 2.19 ms
+    if (chunks <= 0) chunks = 12;  // measured on B200 / PCIe Gen5 (config 2, y stored straight into pinned memory): 6 / 8 / 12 / 16 / 24 / 32 chunks -> 1.85 / 1.78 / 1.72 / 1.78 / 1.82 / 1.81 ms (through a staging buffer + cudaMemcpyAsync per chunk: 1.88 / 1.84 / 1.83 / 1.88 / 2.03 / 2.18 ms)
     // chunk boundaries on multiples of 1024 rows / entries: TMA slices and copies stay 16-byte aligned
     auto round_up = [](long long v, long long m) { return (v + m - 1) / m * m; };
     p->chunk_rows = static_cast<int>(std::max<long long>(1024, round_up((static_cast<long long>(p->rows) + chunks - 1) / chunks, 1024)));
