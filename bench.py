@@ -586,8 +586,10 @@ def run_product_arm(args):
         tag = "_relabelled" if relabelled else ""
         graph_name = f"R-MAT scale {scale} x16, d=0.85" + (", vertex ids relabelled (Graph500-style)" if relabelled
                                                           else ", no vertex permutation")
-        # a PageRank shard also updates and sends every owned row, so rows weigh more than in plain SpMV
-        weight = args.row_weight if args.row_weight >= 0 else (1 if world == 1 or relabelled else 4)
+        # a PageRank shard also updates and sends every owned row, so rows weigh more than in plain SpMV: the
+        # local step costs nnz + 2.25 per row (scripts/shard_balance.py); with the 8-way exchange 4 measured best
+        # (w = 1 / 2 / 4 / 8 -> 995 / 1132 / 1154 / 920 iter/s)
+        weight = args.row_weight if args.row_weight >= 0 else (1 if world == 1 or relabelled else (2 if world == 2 else 4))
         log(f"PageRank {graph_name}: build shard (work(row) = nnz + {weight})")
         n, bounds, srp, sci, sva, n_edges = gen.rmat_pagerank_shard(scale, 16, seed, rank, world, dev, row_weight=weight,
                                                                     relabelled=relabelled)

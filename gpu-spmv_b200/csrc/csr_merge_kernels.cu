@@ -245,20 +245,9 @@ merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
     // combine(earlier, later) = (fe | fl, fl ? vl : ve + vl)
     const int lane = tid & 31, warp = tid >> 5;
     float v = running;
-    int f = emitted ? 1 : 0;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const float pv = __shfl_up_sync(0xffffffffu, v, d);
-        const int pf = __shfl_up_sync(0xffffffffu, f, d);
-        if (lane >= d) {
-            if (!f) v = pv + v;
-            f |= pf;
-        }
-    }
-    // exclusive prefix inside the warp
-    float ex_v = __shfl_up_sync(0xffffffffu, v, 1);
-    int ex_f = __shfl_up_sync(0xffffffffu, f, 1);
-    if (lane == 0) { ex_v = 0.0f; ex_f = 0; }
+    int f, ex_f;
+    float ex_v;
+    warp_segmented_scan(v, emitted, lane, f, ex_v, ex_f);
     if (lane == 31) { s_warp_val[warp] = v; s_warp_flag[warp] = f; }
     __syncthreads();
     // fold the aggregates of the preceding warps

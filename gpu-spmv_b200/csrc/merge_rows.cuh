@@ -31,6 +31,27 @@ __device__ __forceinline__ int2 diagonal_search_global(int diagonal, const int* 
     return make_int2(lo, diagonal - lo);
 }
 
+// ------------------------------------------------- warp segmented scan ----
+// Inclusive segmented scan of `v` over a warp; a lane with `head` starts a segment.  The head flags
+// travel in ONE ballot and every lane derives from the mask how far back it may reach, so only the
+// values are shuffled: 6 SHFL per warp instead of 12 (shuffles share the L1 data pipe with the x
+// gathers, profiles/r1_hub_kernel.md).  Same additions in the same order as the (value, flag) form.
+// f_incl: a head at or before this lane; ex_v / ex_f: the exclusive prefix (lane 0: 0 / 0).
+__device__ __forceinline__ void warp_segmented_scan(float& v, bool head, int lane, int& f_incl, float& ex_v, int& ex_f) {
+    const unsigned mask = __ballot_sync(0xffffffffu, head);
+    const unsigned upto = mask & (0xffffffffu >> (31 - lane));  // heads in lanes 0..lane
+    const int reach = upto ? 31 - __clz(upto) : 0;              // first lane of this lane's segment
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float pv = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane - d >= reach) v = pv + v;
+    }
+    f_incl = upto ? 1 : 0;
+    ex_v = __shfl_up_sync(0xffffffffu, v, 1);
+    ex_f = (mask & ((1u << lane) - 1u)) ? 1 : 0;
+    if (lane == 0) ex_v = 0.0f;
+}
+
 // -------------------------------------------------------------- epilogues ----
 
 struct NoSums {

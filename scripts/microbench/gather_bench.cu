@@ -53,6 +53,77 @@ __global__ void __launch_bounds__(1024, 1) k_global(const uint32_t* __restrict__
     if (acc == 123.456f) out[0] = acc;
 }
 
+// (a2) the same gathers while 8 more bytes per gather are STREAMED, as the matrix stream of an SpMV is:
+// MODE 1 = by the gathering threads themselves (two more coalesced 4-byte loads per gather: the stream
+// shares the LSU / L1 miss path with the gathers), MODE 2 = by 1-D TMA bulk copies into a shared-memory ring
+// issued by one thread (async proxy: the stream does not pass through the LSU).  Question: is the
+// ~1 sector per clock and SM of random L2 gathers a limit of the SM's LSU miss path (then TMA staging of the
+// stream frees it) or of the L2 (then it does not)?
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) k_global_stream(const uint32_t* __restrict__ idx, size_t n, const float* __restrict__ x,
+                                                           const float* __restrict__ s1, const float* __restrict__ s2, float* out) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    constexpr int kStage = 2 * 1024 * U * 4;  // bytes of s1 + s2 one CTA iteration covers (8 B per gather)
+    __shared__ __align__(8) unsigned long long bars[2];
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    if (MODE == 2 && threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    float acc = 0.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+    int it = 0;
+    auto issue = [&](size_t i0_cta, int stage) {  // thread 0: both streams of one CTA iteration -> ring[stage]
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + stage * kStage);
+        const uint32_t bar = bar0 + 8 * stage;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(kStage) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(s1 + i0_cta), "r"(kStage / 2), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst + kStage / 2), "l"(s2 + i0_cta), "r"(kStage / 2), "r"(bar) : "memory");
+    };
+    const size_t first = (size_t)blockIdx.x * blockDim.x * U;
+    if (MODE == 2 && threadIdx.x == 0) {
+        if (first + 1024 * U <= n) issue(first, 0);
+        if (first + stride + 1024 * U <= n) issue(first + stride, 1);
+    }
+    for (size_t base = first; base + 1024 * U <= n; base += stride, ++it) {
+        const size_t i0 = base + threadIdx.x;
+        uint32_t c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) c[u] = __ldcs(idx + i0 + u * blockDim.x);
+        float v[U];
+        if (MODE == 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = __ldcs(s1 + i0 + u * blockDim.x) + __ldcs(s2 + i0 + u * blockDim.x);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += __ldg(x + c[u]);
+        if (MODE == 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc += v[u];
+        }
+        if (MODE == 2) {
+            const int stage = it & 1;
+            const uint32_t bar = bar0 + 8 * stage, parity = (it >> 1) & 1;
+            asm volatile("{\n.reg .pred p;\nW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D;\nbra W;\nD:\n}\n"
+                         :: "r"(bar), "r"(parity) : "memory");
+            const float* sv = reinterpret_cast<const float*>(ring + stage * kStage);
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc += sv[threadIdx.x + u * 1024] + sv[1024 * U + threadIdx.x + u * 1024];
+            __syncthreads();
+            const size_t nxt = base + 2 * stride;
+            if (threadIdx.x == 0 && nxt + 1024 * U <= n) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(nxt, stage);
+            }
+        }
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
+
 // (b) shared-memory table (entries floats), filled from x[0..entries)
 __global__ void __launch_bounds__(1024, 1) k_smem(const uint32_t* __restrict__ idx, size_t n, const float* __restrict__ x, int entries, float* out) {
     extern __shared__ float tab[];
@@ -161,6 +232,19 @@ int main() {
                 report(name, time_ms([&] { k_global<<<2 * sms, 1024>>>(idx, n, x, out); }), sms);
             }
         }
+    }
+    // ---- (a2) gathers + an 8 B/gather stream: by LDG of the gathering threads vs by TMA bulk copies
+    {
+        float *s1, *s2;
+        CK(cudaMalloc(&s1, n * 4)); CK(cudaMalloc(&s2, n * 4));
+        fill<<<1184, 256>>>(s1, n); fill<<<1184, 256>>>(s2, n);
+        make_idx<<<1184, 256>>>(idx, n, 1u << 24, 0);
+        const int ring_bytes = 2 * 2 * 1024 * U * 4;
+        CK(cudaFuncSetAttribute(k_global_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
+        report("global  footprint 65536 KB, gathers only (again)", time_ms([&] { k_global<<<sms, 1024>>>(idx, n, x, out); }), sms);
+        report("global  footprint 65536 KB + 8 B/gather stream by LDG", time_ms([&] { k_global_stream<1><<<sms, 1024>>>(idx, n, x, s1, s2, out); }), sms);
+        report("global  footprint 65536 KB + 8 B/gather stream by TMA", time_ms([&] { k_global_stream<2><<<sms, 1024, ring_bytes>>>(idx, n, x, s1, s2, out); }), sms);
+        CK(cudaFree(s1)); CK(cudaFree(s2));
     }
     // ---- (b) local smem table
     for (int entries : {8192, 24576, 49152}) {

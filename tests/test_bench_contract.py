@@ -49,3 +49,41 @@ def test_committed_product_lines_have_every_contract_key():
             cb = d["cpu_baseline"]
             assert cb["kind"] == "reference" and cb["cores"] == 1 and cb["value"] > 0 and cb["sample"]
             assert r["traffic"] is not None
+
+
+def test_round2_lines_carry_the_sharded_path_and_its_parity():
+    """Round 2: the PageRank / R-MAT figures are top-level scalars (also inside `config`, which the driver keeps
+    whole) and every line carries a `parity` block that was green when the line was printed."""
+    ref_cfg_keys = {"workload", "rows", "nnz", "bytes_per_step", "l2", "parallelism"}
+    for name, n in (("bench_r2_n1.json", 1), ("bench_r2_n2.json", 2), ("bench_r2_n8_first.json", 8)):
+        d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        assert (BASE_KEYS | {"clocks", "roofline", "parity"}) <= set(d), name
+        assert d["n_gpus"] == n and d["parity"]["ok"] is True
+        for key in ("pagerank_iters_per_s", "pagerank_ms_per_iter", "pagerank_exchange", "rmat24_merge_frac"):
+            assert key in d and key in d["config"], (name, key)
+        assert ref_cfg_keys <= set(d["config"])
+        pr20 = d["parity"]["pagerank_scale20"]
+        assert pr20["ok"] and pr20["l1_vs_oracle_f64_max_over_transports"] <= 1e-6 and pr20["transports_bit_identical"]
+        if n > 1:
+            assert set(pr20["transports"]) == {"multicast", "p2p", "nccl"}
+            assert d["parity"]["pagerank_scale26"]["ranks_bit_equal_across_gpus"] is True
+            assert d["pagerank_speedup_vs_1gpu"] == round(d["pagerank_iters_per_s"] / d["pagerank_1gpu_iters_per_s"], 4) or \
+                abs(d["pagerank_speedup_vs_1gpu"] - d["pagerank_iters_per_s"] / d["pagerank_1gpu_iters_per_s"]) < 1e-2
+        else:
+            assert d["cpu_baseline"]["parity_checked"] is True
+            assert d["parity"]["config2_ell_bit_identical_to_cpu_reference"] is True
+            assert d["config2_csr_frac"] >= 0.95  # the drop-in spmv_csr on config 2
+    d8 = json.loads(open(os.path.join(ROOT, "profiles", "bench_r2_n8_first.json")).read().strip().splitlines()[-1])
+    assert d8["pagerank_speedup_vs_1gpu"] >= 6.0  # north_star: >= 6x from 1 to 8 GPUs on R-MAT 26
+
+
+def test_both_arms_describe_the_same_workload():
+    """same_config: the reference arm and the product arm at N = 1 print the same workload string and the same
+    base keys / values in `config` (the product arm adds its measured scalars)."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    ref = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][0])
+    mine = json.loads(open(os.path.join(ROOT, "profiles", "bench_r2_n1.json")).read().strip().splitlines()[-1])
+    for key in ("workload", "rows", "nnz", "bytes_per_step", "l2", "parallelism"):
+        assert ref["config"][key] == mine["config"][key], key
+    assert ref["metric"] == mine["metric"] and ref["unit"] == mine["unit"]
