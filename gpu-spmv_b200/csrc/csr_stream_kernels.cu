@@ -775,8 +775,9 @@ cudaError_t launch_short(const CsrView& A, const float* x, float* y, cudaStream_
     const double avg = static_cast<double>(A.nnz) / A.rows;
     if (avg <= 2.6) return launch_short_as<4, 2, 1536>(A, x, y, stream);    // 512-row windows
     if (avg <= 5.2) return launch_short_as<6, 1, 1536>(A, x, y, stream);    // 256-row windows, 8 CTAs per SM
-    if (avg <= 10.5) return launch_short_as<8, 1, 3072>(A, x, y, stream);   // 4 CTAs per SM
-    return launch_short_as<8, 1, 5120>(A, x, y, stream);                    // up to ~17 per row, 2 CTAs per SM
+    return launch_short_as<8, 1, 3072>(A, x, y, stream);                    // avg <= 10.5: 4 CTAs per SM
+    // (a 5120-entry stage for avg <= 16 leaves 2 CTAs per SM and loses to the general ring: 13-point stencil
+    //  0.109 against 0.092 ms, scripts/time_mid.py)
 }
 
 // Short rows only: a row is walked by one thread, and a window that does not fit a stage is walked
@@ -786,8 +787,13 @@ bool short_eligible(const CsrView& A, cudaStream_t stream) {
     if (mode == 0) return false;
     if (mode == 1) return true;
     const double avg = static_cast<double>(A.nnz) / A.rows;
-    if (avg > 16.0) return false;  // launch_short's largest stage
-    return longest_row_cached(A, stream) <= 64;
+    if (avg > 10.5) return false;  // launch_short's largest stage
+    // UNIFORM rows only (stencils, meshes, banded systems: longest <= avg + 1.5): there the lean loop wins
+    // (config 2: 0.129 against 0.164 ms).  On rows of random length 0 .. 2 avg with random columns it LOSES to
+    // the general ring (scripts/time_mid.py, 4 M rows: avg 5 0.159 against 0.103 ms, avg 8 0.250 against
+    // 0.158 ms): a warp waits for its longest row in batches of U dependent gathers, and 32 registers leave
+    // fewer gathers in flight per thread than the general ring's 63.
+    return static_cast<double>(longest_row_cached(A, stream)) <= avg + 1.5;
 }
 
 bool pipe_eligible(const CsrView& A) {
@@ -846,7 +852,7 @@ cudaError_t launch_csr_warp_per_row(const CsrView& A, const float* x, float* y, 
 }
 
 // lanes per row for VECTOR_CSR from the average row length:
-// <6 -> 1, <8 -> 2, <16 -> 4, <32 -> 8, <64 -> 16, else a full warp.
+// <20 -> 1, <32 -> 8, <64 -> 16, else a full warp.
 // One lane per row IS the row-owner pipeline of SCALAR_CSR (sequential order): on rows this short
 // sharing a row between lanes only adds shuffles -- config 2 (5 per row): 0.165 ms against 0.183 ms
 // with two lanes.  The selector only sends matrices with max <= 10 * (min + 1) here, so no lane is
@@ -855,9 +861,10 @@ int vector_lanes_for(int rows, int nnz) {
     static const int forced = stream_env_int("SPMV_B200_VECTOR_LANES", 0);
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
     const double avg = rows > 0 ? static_cast<double>(nnz) / rows : 0.0;
-    if (avg < 6.0) return 1;
-    if (avg < 8.0) return 2;
-    if (avg < 16.0) return 4;
+    // measured on 4 M-row matrices (scripts/time_mid.py), one lane against the old choice of 2 / 4 / 8 lanes:
+    // 7-point stencil 0.052 / 0.062 ms, 9-point 0.060 / 0.088, 13-point 0.092 / 0.116, random rows avg 8
+    // 0.158 / 0.258, avg 12 0.228 / 0.247, avg 16 0.302 / 0.313, avg 24 0.745 / 0.478 -> one lane below 20
+    if (avg < 20.0) return 1;
     if (avg < 32.0) return 8;
     if (avg < 64.0) return 16;
     return 32;
