@@ -652,11 +652,17 @@ void pipe_geometry(const CsrView& A, int& rpg, int& cap) {
 // Longest row of a device CSR, computed once per (row_ptrs array, shape) with one pass over
 // row_ptrs and remembered.  It only steers the choice between two correct kernels, so a stale
 // entry (the array was rewritten in place) costs speed, never correctness.
+std::mutex& longest_mu() { static std::mutex mu; return mu; }
+std::unordered_map<unsigned long long, int>& longest_cache() { static std::unordered_map<unsigned long long, int> c; return c; }
+unsigned long long longest_key(const int* d_row_ptrs, int rows, int nnz) {
+    return (reinterpret_cast<uintptr_t>(d_row_ptrs) * 0x9E3779B97F4A7C15ull) ^ (static_cast<unsigned long long>(rows) << 32) ^
+           static_cast<unsigned>(nnz);
+}
+
 int longest_row_cached(const CsrView& A, cudaStream_t stream) {
-    static std::mutex mu;
-    static std::unordered_map<unsigned long long, int> cache;
-    const unsigned long long key = (reinterpret_cast<uintptr_t>(A.row_ptrs) * 0x9E3779B97F4A7C15ull) ^
-                                   (static_cast<unsigned long long>(A.rows) << 32) ^ static_cast<unsigned>(A.nnz);
+    std::mutex& mu = longest_mu();
+    std::unordered_map<unsigned long long, int>& cache = longest_cache();
+    const unsigned long long key = longest_key(A.row_ptrs, A.rows, A.nnz);
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find(key);
@@ -817,6 +823,22 @@ cudaError_t launch_best_lpr(const CsrView& A, const float* x, float* y, cudaStre
 }
 
 }  // namespace
+
+// csr_to_gpu knows the host row_ptrs: it seeds the longest-row cache so that the first stream-ordered
+// SCALAR / VECTOR launch on an uploaded matrix neither allocates nor synchronises (the lazy device pass
+// remains for device arrays supplied by the caller); csr_free_gpu / csr_to_gpu drop the entry.
+void seed_longest_row(const int* d_row_ptrs, int rows, int nnz, int longest) {
+    if (!d_row_ptrs) return;
+    std::lock_guard<std::mutex> lock(longest_mu());
+    auto& cache = longest_cache();
+    if (cache.size() > 4096) cache.clear();
+    cache[longest_key(d_row_ptrs, rows, nnz)] = longest;
+}
+void forget_longest_row(const int* d_row_ptrs, int rows, int nnz) {
+    if (!d_row_ptrs) return;
+    std::lock_guard<std::mutex> lock(longest_mu());
+    longest_cache().erase(longest_key(d_row_ptrs, rows, nnz));
+}
 
 cudaError_t launch_csr_stream(const CsrView& A, const float* x, float* y, int lanes_per_row,
                               cudaStream_t stream) {

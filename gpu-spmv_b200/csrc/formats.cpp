@@ -171,6 +171,12 @@ int csr_to_gpu(CSRMatrix* m) {
     CUDA_CHECK(cudaMemcpy(m->d_row_ptrs, m->row_ptrs, nptr * sizeof(int), cudaMemcpyHostToDevice));
     m->owns_device_memory = true;
     b200::note_device_csr(m);  // spmv_csr(MERGE_PATH) may attach a column plan to this upload
+    {   // the row-owner launchers steer by the longest row: known here for free, so the first
+        // stream-ordered launch on this upload does not have to measure it (allocate + synchronise)
+        int longest = 0;
+        for (int r = 0; r < m->num_rows; ++r) longest = std::max(longest, m->row_ptrs[r + 1] - m->row_ptrs[r]);
+        b200::seed_longest_row(m->d_row_ptrs, m->num_rows, m->nnz, longest);
+    }
     return kOk;
 }
 
@@ -191,6 +197,7 @@ int csr_from_gpu(CSRMatrix* m) {
 void csr_free_gpu(CSRMatrix* m) {
     if (!m) return;
     b200::forget_device_csr(m->d_col_indices);
+    b200::forget_longest_row(m->d_row_ptrs, m->num_rows, m->nnz);
     if (m->d_values) cudaFree(m->d_values);
     if (m->d_col_indices) cudaFree(m->d_col_indices);
     if (m->d_row_ptrs) cudaFree(m->d_row_ptrs);

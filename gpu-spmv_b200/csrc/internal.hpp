@@ -134,6 +134,9 @@ cudaError_t launch_csr_warp_per_row(const CsrView& A, const float* x, float* y, 
 // VECTOR_CSR front end: picks lanes per row from the average row length.
 cudaError_t launch_csr_vector(const CsrView& A, const float* x, float* y, cudaStream_t stream);
 int vector_lanes_for(int rows, int nnz);
+// longest-row cache of the row-owner launchers (csr_stream_kernels.cu), keyed by the device row_ptrs array
+void seed_longest_row(const int* d_row_ptrs, int rows, int nnz, int longest);
+void forget_longest_row(const int* d_row_ptrs, int rows, int nnz);
 
 // Merge-path: partition (fills plan.coords) then tile + fix-up kernels.
 cudaError_t launch_merge_partition(const CsrView& A, const MergePlan& plan, cudaStream_t stream);

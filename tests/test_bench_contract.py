@@ -55,7 +55,7 @@ def test_round2_lines_carry_the_sharded_path_and_its_parity():
     """Round 2: the PageRank / R-MAT figures are top-level scalars (also inside `config`, which the driver keeps
     whole) and every line carries a `parity` block that was green when the line was printed."""
     ref_cfg_keys = {"workload", "rows", "nnz", "bytes_per_step", "l2", "parallelism"}
-    for name, n in (("bench_r2_n1.json", 1), ("bench_r2_n2.json", 2), ("bench_r2_n8_first.json", 8)):
+    for name, n in (("bench_r2_n1.json", 1), ("bench_r2_n2.json", 2), ("bench_r2_n8.json", 8)):
         d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
         assert (BASE_KEYS | {"clocks", "roofline", "parity"}) <= set(d), name
         assert d["n_gpus"] == n and d["parity"]["ok"] is True
@@ -73,7 +73,7 @@ def test_round2_lines_carry_the_sharded_path_and_its_parity():
             assert d["cpu_baseline"]["parity_checked"] is True
             assert d["parity"]["config2_ell_bit_identical_to_cpu_reference"] is True
             assert d["config2_csr_frac"] >= 0.95  # the drop-in spmv_csr on config 2
-    d8 = json.loads(open(os.path.join(ROOT, "profiles", "bench_r2_n8_first.json")).read().strip().splitlines()[-1])
+    d8 = json.loads(open(os.path.join(ROOT, "profiles", "bench_r2_n8.json")).read().strip().splitlines()[-1])
     assert d8["pagerank_speedup_vs_1gpu"] >= 6.0  # north_star: >= 6x from 1 to 8 GPUs on R-MAT 26
 
 
