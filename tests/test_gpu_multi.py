@@ -84,3 +84,50 @@ def test_sharded_pagerank_nccl_and_fused_exchange(sp, orc, cuda, tmp_path, scale
     iters = int(meta[0][0])
     o_same, _, l2, l1, conv = orc.pagerank_f64(n, n, rp.numpy(), ci.numpy(), va.numpy(), 0.85, 1e-6, 100, fixed_it=iters)
     assert bool(meta[0][2]) and np.abs(ranks[0].astype(np.float64) - o_same).sum() <= 1e-6
+
+
+# ---- the native path (csrc/pagerank_dist.cu): C++ rendezvous, symmetric buffers, in-kernel barrier ----
+
+def test_native_pagerank_multi_transports_bit_identical(sp, orc, cuda):
+    """spmv_b200_pagerank_multi on the GPUs of the box (one process, one host thread per device): multicast,
+    peer stores and NCCL must give bit-identical vectors, within L1 1e-6 of the f64 oracle restatement."""
+    import ctypes as C
+    import gpu_spmv_b200.dist as D
+    import gpu_spmv_b200.gen as gen
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n, rp, ci, va = gen.rmat_pagerank_csr(18, 16, 7, "cpu")
+    rp_n, ci_n, va_n = rp.numpy(), ci.numpy(), va.numpy()
+    A = sp.csr_from_arrays(n, n, rp_n, ci_n, va_n)
+    iters = 10
+    cfg = sp.make_pagerank_config(0.85, 0.0, iters)
+    o_ranks = orc.pagerank_f64(n, n, rp_n, ci_n, va_n, 0.85, 1e-6, 100, fixed_it=iters)[0]
+    results = {}
+    for name, exchange in (("auto", D.EXCHANGE_AUTO), ("p2p", D.EXCHANGE_P2P), ("nccl", D.EXCHANGE_NCCL)):
+        ranks = np.empty(n, np.float32)
+        res = D.PrDistResult()
+        rc = sp.lib.spmv_b200_pagerank_multi(A, C.byref(cfg), world, None, exchange, 4, iters,
+                                             ranks.ctypes.data_as(C.c_void_p), C.byref(res))
+        assert rc == 0, (name, sp.spmv_error_string(rc))
+        assert res.iterations == iters
+        assert float(np.abs(ranks.astype(np.float64) - o_ranks.astype(np.float64)).sum()) <= 1e-6, name
+        results[name] = (ranks, res.exchange)
+    print("transports used:", {k: D.EXCHANGE_NAMES[v[1]] for k, v in results.items()})
+    assert np.array_equal(results["auto"][0].view(np.uint32), results["p2p"][0].view(np.uint32))
+    assert np.array_equal(results["auto"][0].view(np.uint32), results["nccl"][0].view(np.uint32))
+    sp.csr_destroy(A)
+
+
+def test_plain_c_caller_of_the_multi_gpu_entry_point(cuda):
+    """tests/c/pagerank_multi_test.c: a C program linked against libspmv_b200.so, no Python in the loop."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "c", "_build", "pagerank_multi_test")
+    if not os.path.exists(exe):
+        pytest.skip("tests/c/_build/pagerank_multi_test not built (run __graft_entry__.build())")
+    for exchange in ("-1", "1", "0"):
+        p = subprocess.run([exe, "2", "16", exchange], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert p.returncode == 0 and "PASS" in p.stdout, p.stdout[-2000:]

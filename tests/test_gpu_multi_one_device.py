@@ -109,3 +109,16 @@ def test_rejects_bad_device_lists(sp, cuda):
     rc = sp.lib.spmv_b200_pagerank_multi(A, C.byref(cfg), 9, None, 1, 4, 0, out.ctypes.data_as(C.c_void_p), C.byref(res))
     assert rc == int(sp.SpMVError.INVALID_ARGUMENT)
     sp.csr_destroy(A)
+
+
+def test_plain_c_caller_single_gpu(cuda):
+    """tests/c/pagerank_multi_test.c (a C program linked against libspmv_b200.so through include/spmv_b200.h,
+    no Python in the loop) with n_gpus = 1: spmv_b200_pagerank_multi against the drop-in spmv_b200_pagerank."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "c", "_build", "pagerank_multi_test")
+    if not os.path.exists(exe):
+        pytest.skip("tests/c/_build/pagerank_multi_test not built (run __graft_entry__.build())")
+    p = subprocess.run([exe, "1", "15"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert p.returncode == 0 and "PASS" in p.stdout, p.stdout[-2000:]
