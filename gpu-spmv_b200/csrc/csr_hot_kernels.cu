@@ -49,7 +49,10 @@ namespace {
 
 constexpr int kWorkers = 4;
 constexpr int kHotThreads = kWorkers * kT;  // 1024
-constexpr int kBuf = kTile + 8;             // words per worker: product span (padded to 4), then row ends
+// words per worker: product span (padded to 4), then row ends.  The tile is 256 * IPT merge items, IPT = 7 or 8
+// chosen per matrix by merge_items_for() -- the SAME choice as the plain tile kernel's, so that a plan stays
+// bit-identical to spmv_csr(MERGE_PATH) on every matrix.
+constexpr int hot_buf_words(int ipt) { return kT * ipt + 8; }
 constexpr int kWarps = kT / 32;             // warps per worker
 constexpr int kCountBuckets = 65536;
 
@@ -95,13 +98,15 @@ __device__ __forceinline__ float gather_enc(int e, uint32_t s_hot_addr, const fl
 
 // One tile's share of the matrix stream held by a thread: kIPT single non-zeros, lane-consecutive
 // (a warp-wide gather covers 32 ADJACENT non-zeros; 32-bit loads, so no alignment requirement).
+template <int IPT>
 struct StreamRegs {
-    float v[kIPT];
-    int c[kIPT];
+    float v[IPT];
+    int c[IPT];
 };
 
 // l2_mode bit 0: the stream is loaded with L2::evict_first (read once; must not displace x in L2)
-__device__ __forceinline__ void load_stream(StreamRegs& s, int nz_s, int nz_e, int wt,
+template <int kIPT>
+__device__ __forceinline__ void load_stream(StreamRegs<kIPT>& s, int nz_s, int nz_e, int wt,
                                             const float* __restrict__ values, const int* __restrict__ enc,
                                             unsigned l2_mode, uint64_t pol_first) {
     if (l2_mode & 1u) {
@@ -150,7 +155,10 @@ __device__ __forceinline__ void worker_store_sums(const NoSums&, double*, int, d
 
 // Shared memory: [hot table: hot_slots floats][kWorkers x kBuf words][kWorkers x kWarps x 3 doubles]
 //                [kWorkers x kWarps floats][kWorkers x kWarps ints]
-constexpr size_t kHotFixedSmem = static_cast<size_t>(kWorkers) * kBuf * 4 + kWorkers * kWarps * (3 * 8 + 4 + 4);
+constexpr size_t hot_fixed_smem(int ipt) {
+    return static_cast<size_t>(kWorkers) * hot_buf_words(ipt) * 4 + kWorkers * kWarps * (3 * 8 + 4 + 4);
+}
+constexpr size_t kHotFixedSmem = hot_fixed_smem(8);  // the larger geometry: what the table capacity is sized against
 
 // One CTA per SM (64 registers per thread); the next tile's stream is loaded into registers while
 // the current tile is reduced.  (Two CTAs of 32 registers per SM spill and measured 1.7x slower.)
@@ -162,13 +170,15 @@ constexpr size_t kHotFixedSmem = static_cast<size_t>(kWorkers) * kBuf * 4 + kWor
 // step unchanged: more gathers in flight only lengthen the queue in front of the L1 miss path, which is
 // what the kernel is bound by (scripts/microbench/gather_bench.cu: L2-resident gathers retire at 1 per clock
 // and SM, L1-resident ones at 2.3, shared-memory ones at 4.4).
-template <class Row, bool ALL_HOT>
+template <class Row, bool ALL_HOT, int IPT>
 __global__ void __launch_bounds__(kHotThreads, 1)
 merge_hot_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int* __restrict__ enc,
                  const float* __restrict__ values, const float* __restrict__ x,
                  const int* __restrict__ hot_cols, int n_hot, const int2* __restrict__ coords, int num_tiles,
                  int* __restrict__ carry_row, float* __restrict__ carry_val, Row row_op,
                  double* __restrict__ partials, unsigned l2_mode) {
+    constexpr int kIPT = IPT;  // shadow the file-level geometry: this kernel's tile is kT * IPT items
+    constexpr int kBuf = kT * IPT + 8;  // == hot_buf_words(IPT)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint64_t pol_first = dev::l2_policy_evict_first();
     const uint64_t pol_last = dev::l2_policy_evict_last();
@@ -197,7 +207,7 @@ merge_hot_kernel(int rows, int nnz, const int* __restrict__ row_ptrs, const int*
     const float row_ctx = row_op.prepare();
 
     int2 c0 = make_int2(0, 0), c1 = c0;
-    StreamRegs cur;
+    StreamRegs<IPT> cur;
     if (tile < num_tiles) {
         c0 = __ldg(coords + tile);
         c1 = __ldg(coords + tile + 1);
@@ -445,13 +455,13 @@ int device_sms() {
     return sms;
 }
 
-template <class Row, bool ALL_HOT>
+template <class Row, bool ALL_HOT, int IPT>
 cudaError_t run_hot_variant(const CsrView& A, const HotPlan& hot, const float* x, const MergePlan& plan,
                             const Row& row_op, cudaStream_t stream, int* grid_out) {
     const int sms = device_sms();
     const int n_hot = ALL_HOT ? A.cols : hot.n_hot;
-    const size_t smem = static_cast<size_t>((n_hot + 3) & ~3) * 4 + kHotFixedSmem;
-    auto kernel = merge_hot_kernel<Row, ALL_HOT>;
+    const size_t smem = static_cast<size_t>((n_hot + 3) & ~3) * 4 + hot_fixed_smem(IPT);
+    auto kernel = merge_hot_kernel<Row, ALL_HOT, IPT>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     // L2 priorities (bit 0: stream evict_first, bit 1: x gathers evict_last).  Default: on when x does not
@@ -473,8 +483,14 @@ cudaError_t run_hot_variant(const CsrView& A, const HotPlan& hot, const float* x
 template <class Row>
 cudaError_t run_hot(const CsrView& A, const HotPlan& hot, const float* x, const MergePlan& plan, const Row& row_op,
                     cudaStream_t stream, int* grid_out) {
-    if (hot.all_hot) return run_hot_variant<Row, true>(A, hot, x, plan, row_op, stream, grid_out);
-    return run_hot_variant<Row, false>(A, hot, x, plan, row_op, stream, grid_out);
+    // 8-item tiles exist for the plain product only (the PageRank plans are always cut at 7 items)
+    if (!Row::kReduces && plan.ipt == 8) {
+        if (hot.all_hot) return run_hot_variant<Row, true, (Row::kReduces ? kIPT : 8)>(A, hot, x, plan, row_op, stream, grid_out);
+        return run_hot_variant<Row, false, (Row::kReduces ? kIPT : 8)>(A, hot, x, plan, row_op, stream, grid_out);
+    }
+    if (plan.ipt != kIPT) return cudaErrorInvalidValue;
+    if (hot.all_hot) return run_hot_variant<Row, true, kIPT>(A, hot, x, plan, row_op, stream, grid_out);
+    return run_hot_variant<Row, false, kIPT>(A, hot, x, plan, row_op, stream, grid_out);
 }
 
 }  // namespace

@@ -58,9 +58,10 @@ size_t merge_plan_bytes(int rows, int nnz, bool with_partials) {
     return b + 256;
 }
 
-MergePlan merge_plan_carve(void* block, int rows, int nnz, bool with_partials) {
+MergePlan merge_plan_carve(void* block, int rows, int nnz, bool with_partials, int ipt) {
     MergePlan p;
-    p.num_tiles = merge_num_tiles(rows, nnz);
+    p.ipt = ipt;
+    p.num_tiles = merge_num_tiles(rows, nnz, ipt);
     p.fixup_blocks = fixup_blocks_for(p.num_tiles);
     const size_t tiles = static_cast<size_t>(p.num_tiles);
     unsigned char* at = static_cast<unsigned char*>(block);
@@ -77,11 +78,11 @@ MergePlan merge_plan_carve(void* block, int rows, int nnz, bool with_partials) {
 namespace {
 
 __global__ void merge_partition_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
-                                       int num_tiles, int2* __restrict__ coords) {
+                                       int num_tiles, int tile_items, int2* __restrict__ coords) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > num_tiles) return;
     const long long total = static_cast<long long>(rows) + nnz;
-    const long long d = static_cast<long long>(t) * kTile;
+    const long long d = static_cast<long long>(t) * tile_items;
     coords[t] = diagonal_search_global(static_cast<int>(d < total ? d : total), row_ptrs, rows, nnz);
 }
 
@@ -102,13 +103,15 @@ __device__ __forceinline__ void block_store_sums(const NoSums&, double*, int, do
 
 // ---------------------------------------------------------------- level 2 ----
 
-template <class Row>
+template <class Row, int IPT>
 __global__ void __launch_bounds__(kT)
 merge_tile_kernel(int rows, int nnz, const int* __restrict__ row_ptrs,
                   const int* __restrict__ col_indices, const float* __restrict__ values,
                   const float* __restrict__ x, const int2* __restrict__ coords,
                   int* __restrict__ carry_row, float* __restrict__ carry_val, Row row_op,
                   double* __restrict__ partials, int use_tma) {
+    constexpr int kIPT = IPT;          // shadow the file-level geometry: this kernel's tile is kT * IPT items
+    constexpr int kTile = kT * IPT;
     __shared__ __align__(16) int s_end_raw[kTile + 8];  // global END offset of tile-local row i (+ alignment shift)
     __shared__ __align__(16) float s_prod[kTile + 4];   // values, then products in place
     extern __shared__ __align__(16) int s_col[];        // [kTile + 4], allocated for the TMA path only
@@ -339,11 +342,15 @@ cudaError_t run_tiles(const CsrView& A, const float* x, const MergePlan& plan, c
     if (plan.num_tiles <= 0) return cudaSuccess;
     static const int use_tma = merge_env_int("SPMV_B200_MERGE_TMA", 0);
     static const int carveout = merge_env_int("SPMV_B200_MERGE_CARVEOUT", -1);
-    if (carveout >= 0) cudaFuncSetAttribute(merge_tile_kernel<Row>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-    const size_t dyn_smem = use_tma ? (kTile + 4) * sizeof(int) : 0;
-    merge_tile_kernel<Row><<<plan.num_tiles, kT, dyn_smem, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values,
-                                                                     x, plan.coords, plan.carry_row, plan.carry_val,
-                                                                     row_op, plan.partials, use_tma);
+    auto launch = [&](auto kernel, int ipt) {
+        if (carveout >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+        const size_t dyn_smem = use_tma ? (kT * ipt + 4) * sizeof(int) : 0;
+        kernel<<<plan.num_tiles, kT, dyn_smem, stream>>>(A.rows, A.nnz, A.row_ptrs, A.col_indices, A.values, x, plan.coords,
+                                                         plan.carry_row, plan.carry_val, row_op, plan.partials, use_tma);
+    };
+    if (plan.ipt == 8) launch(merge_tile_kernel<Row, 8>, 8);
+    else if (plan.ipt == kMergeItemsPerThread) launch(merge_tile_kernel<Row, kMergeItemsPerThread>, kMergeItemsPerThread);
+    else return cudaErrorInvalidValue;
     merge_fixup_kernel<Row><<<plan.fixup_blocks, 256, 0, stream>>>(plan.num_tiles, plan.carry_row, plan.carry_val,
                                                                    row_op, plan.partials, plan.num_tiles);
     count_launches(2);
@@ -352,10 +359,21 @@ cudaError_t run_tiles(const CsrView& A, const float* x, const MergePlan& plan, c
 
 }  // namespace
 
+int merge_items_for(int rows, int nnz) {
+    static const int forced = merge_env_int("SPMV_B200_MERGE_IPT", 0);  // 7 / 8: A/B timing
+    if (forced == 7 || forced == 8) return forced;
+    // measured (scripts/time_mid.py, bench_hot.py; 7 / 8 items): config 2 0.380 / 0.321 ms, 7-point stencil
+    // 0.129 / 0.102, 9-point 0.154 / 0.134, random rows avg 5 and 8 equal, avg 12-24 0.271 / 0.273 .. 0.488 / 0.498,
+    // config 3 (avg 3) 2.19 / 2.27, R-MAT 24 (avg 16) 1.27 / 1.37 -> 8 items for 4 <= avg < 10 only
+    const double avg = rows > 0 ? static_cast<double>(nnz) / rows : 0.0;
+    return (avg >= 4.0 && avg < 10.0) ? 8 : kMergeItemsPerThread;
+}
+
 cudaError_t launch_merge_partition(const CsrView& A, const MergePlan& plan, cudaStream_t stream) {
     if (plan.num_tiles <= 0) return cudaSuccess;
     const int n = plan.num_tiles + 1;
-    merge_partition_kernel<<<(n + 255) / 256, 256, 0, stream>>>(A.rows, A.nnz, A.row_ptrs, plan.num_tiles, plan.coords);
+    merge_partition_kernel<<<(n + 255) / 256, 256, 0, stream>>>(A.rows, A.nnz, A.row_ptrs, plan.num_tiles, kT * plan.ipt,
+                                                                plan.coords);
     count_launches(1);
     return cudaGetLastError();
 }

@@ -70,11 +70,12 @@ cudaError_t dispatch_csr(const CsrView& A, const float* x, float* y, int kernel_
                 return launch_seg_spmv(A, planned->seg, x, y, stream);
             void* block = scratch.reserve(merge_plan_bytes(A.rows, A.nnz, false));
             if (!block) return cudaErrorMemoryAllocation;
-            const MergePlan plan = merge_plan_carve(block, A.rows, A.nnz, false);
+            const bool hub = planned && planned->hot.n_hot > 0 && planned->hot.nnz == A.nnz && planned->hot.cols == A.cols;
+            // tile geometry by structure (7 or 8 items per thread): the same choice with and without a plan
+            const MergePlan plan = merge_plan_carve(block, A.rows, A.nnz, false, merge_items_for(A.rows, A.nnz));
             cudaError_t e = launch_merge_partition(A, plan, stream);
             if (e != cudaSuccess) return e;
-            if (planned && planned->hot.n_hot > 0 && planned->hot.nnz == A.nnz && planned->hot.cols == A.cols)
-                return launch_hot_spmv(A, planned->hot, x, y, plan, stream);
+            if (hub) return launch_hot_spmv(A, planned->hot, x, y, plan, stream);
             return launch_merge_spmv(A, x, y, plan, stream);
         }
         case SpMVConfig::VECTOR_CSR:
@@ -165,7 +166,7 @@ int csr_plan_create(const CSRMatrix* A, int max_hot_columns, int flags, CsrPlan*
             delete p;
             return static_cast<int>(SpMVError::CUDA_MALLOC);
         }
-        p->merge = merge_plan_carve(block, p->A.rows, p->A.nnz, false);
+        p->merge = merge_plan_carve(block, p->A.rows, p->A.nnz, false, merge_items_for(p->A.rows, p->A.nnz));
         cudaError_t e = cudaSuccess;
         if (flags & kPlanSnapshotValues) {  // uniform matrix -> ELL layout, if the caller accepts a value snapshot
             int width = 0;

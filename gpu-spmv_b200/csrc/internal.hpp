@@ -86,15 +86,22 @@ struct MergePlan {
     float* carry_val = nullptr;  // [num_tiles] its partial sum inside the tile
     double* partials = nullptr;  // [(num_tiles + fixup_blocks) * 3] fused-PageRank sums
     int fixup_blocks = 0;
+    int ipt = kMergeItemsPerThread;  // merge items per thread of the tiles in `coords` (7, or 8 for regular matrices)
 };
 
-inline int merge_num_tiles(int rows, int nnz) {
+inline int merge_num_tiles(int rows, int nnz, int ipt = kMergeItemsPerThread) {
     const long long items = static_cast<long long>(rows) + nnz;
-    return static_cast<int>((items + kMergeTile - 1) / kMergeTile);
+    const long long tile = static_cast<long long>(kMergeThreads) * ipt;
+    return static_cast<int>((items + tile - 1) / tile);
 }
-size_t merge_plan_bytes(int rows, int nnz, bool with_partials);
+// Items per thread of the plain MERGE_PATH tile kernel.  7 (odd: the stride-7 reads of the products are
+// bank-conflict-free) wins on every skewed matrix; on short regular rows (4 <= avg < 10) 8 items = 14 % fewer tiles
+// win (config 2: 0.321 against 0.380 ms).  The hub-column plan follows the same choice (bit-identity with the
+// plain path); PageRank plans and the segmented stream always use 7.
+int merge_items_for(int rows, int nnz);
+size_t merge_plan_bytes(int rows, int nnz, bool with_partials);  // sized for 7 items (the larger tile count)
 // carve a MergePlan out of a scratch block of merge_plan_bytes() bytes
-MergePlan merge_plan_carve(void* block, int rows, int nnz, bool with_partials);
+MergePlan merge_plan_carve(void* block, int rows, int nnz, bool with_partials, int ipt = kMergeItemsPerThread);
 
 // ---- fused PageRank epilogue parameters ---------------------------------------------
 constexpr int kMaxPeers = 8;  // GPUs of one NVSwitch box
