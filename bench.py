@@ -400,6 +400,8 @@ def run_product_arm(args):
     assert sp.lib.spmv_b200_ell_host_plan_create(E, 0, C.byref(host_plan)) == 0
     h2d_bytes, d2h_bytes = C.c_ulonglong(0), C.c_ulonglong(0)
     assert sp.lib.spmv_b200_ell_host_plan_bytes(host_plan, C.byref(h2d_bytes), C.byref(d2h_bytes)) == 0
+    c_gated, c_down = C.c_int(0), C.c_int(0)
+    assert sp.lib.spmv_b200_ell_host_plan_gated(host_plan, C.byref(c_gated), C.byref(c_down)) == 0
 
     def e2e_step():  # blocking: returns when y_host is complete
         rc = sp.lib.spmv_b200_spmv_ell_host(host_plan, x_host.data_ptr(), y_host.data_ptr())
@@ -422,11 +424,15 @@ def run_product_arm(args):
     e2e_sec = wall_time(e2e_step, e2e_steps)
     e2e_same = bool(torch.equal(y_host.view(torch.int32), y_device_path.cpu().view(torch.int32)))
     serial_sec = wall_time(e2e_serial_step, e2e_steps)
+    # still gated after the timed calls (a call whose x did not arrive in time would have fallen back for good)
+    assert sp.lib.spmv_b200_ell_host_plan_gated(host_plan, C.byref(c_gated), None) == 0
+    host_gated, host_down_chunks = bool(c_gated.value), c_down.value
     sp.lib.spmv_b200_ell_host_plan_destroy(host_plan)
     e2e = {"value": world * ell_bytes / e2e_sec / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d_bytes.value) * world,
            "d2h_bytes_per_step": int(d2h_bytes.value) * world, "ms_per_step": e2e_sec * 1e3,
-           "api": "spmv_b200_spmv_ell_host (blocking C ABI, pinned host x -> pinned host y; H2D / kernel / D2H "
-                  "pipelined over row chunks on three streams)",
+           "api": "spmv_b200_spmv_ell_host (blocking C ABI, pinned host x -> pinned host y; " + (
+               "gated form: one upload copy, one persistent kernel consuming x as it lands, %d D2H chunks released by the kernel)" % host_down_chunks
+               if host_gated else "H2D / kernel / D2H pipelined over row chunks on three streams)"),
            "bit_identical_to_device_path": e2e_same,
            "serial_ms_per_step": serial_sec * 1e3}
     parity["e2e_host_call_bit_identical"] = e2e_same

@@ -160,6 +160,8 @@ PROTOTYPES = {
     "spmv_b200_ell_host_plan_destroy": (None, [vp]),
     "spmv_b200_spmv_ell_host": (C.c_int, [vp, vp, vp]),
     "spmv_b200_ell_host_plan_info": (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
+    "spmv_b200_ell_host_plan_gated": (C.c_int, [vp, c_int_p, c_int_p]),
+    "spmv_b200_probe_h2d_order": (C.c_int, [vp, C.c_ulonglong, C.c_int, C.POINTER(C.c_longlong), C.c_int, C.c_uint]),
     "spmv_b200_ell_host_plan_bytes": (C.c_int, [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "spmv_b200_ell_from_csr_device": (C.c_int, [ELL_P, CSR_P]),
     "spmv_b200_merge_path_search": (C.c_int, [C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p]),

@@ -219,6 +219,16 @@ int spmv_b200_ell_host_plan_bytes(const spmv_b200_ell_host_plan* plan, unsigned 
     return 0;
 }
 
+int spmv_b200_ell_host_plan_gated(const spmv_b200_ell_host_plan* plan, int* gated, int* x_chunks) {
+    if (!plan) return kBadArg;
+    b200::ell_host_plan_gated(reinterpret_cast<const b200::EllHostPlan*>(plan), gated, x_chunks);
+    return 0;
+}
+
+int spmv_b200_probe_h2d_order(const float* x_host, unsigned long long n, int samples, long long* out_ns, int mode, unsigned sleep_ns) {
+    return guarded([&] { return b200::probe_h2d_order(x_host, static_cast<size_t>(n), samples, out_ns, mode, sleep_ns); });
+}
+
 // ---- D. bandwidth / PageRank / benchmark ------------------------------------------------
 int spmv_b200_bandwidth_csr(const spmv_b200_csr* A, float ms, spmv_b200_bandwidth* out) {
     if (!out) return kBadArg;

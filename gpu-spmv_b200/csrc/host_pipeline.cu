@@ -14,10 +14,20 @@
 // degenerates to H2D, then compute overlapped with D2H -- never worse than the serial form.
 // Numerics: the row chunks run the same ELL kernel (ell_tma_pipe_kernel<1>) on the same rows, so
 // y is bit-identical to spmv_ell / spmv_cpu_ell.
+//
+// Default form (the "chunked" form above stays as SPMV_B200_HOST_GATED=0 and as the fall-back): the
+// GATED form of ell_gated_kernel.cu -- ONE upload copy, ONE persistent kernel that consumes x while it
+// arrives (the data is its own arrival flag), and one stream-ordered wait + D2H copy per row chunk
+// queued before the launch, released by progress counters the kernel advances.  Measurements:
+// profiles/r2_host_gated.txt.
 #include "internal.hpp"
 
+#include <cuda.h>
+
 #include <algorithm>
+#include <chrono>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -27,6 +37,18 @@ namespace b200 {
 
 cudaError_t launch_ell_rows(int rows, int width, const int* col_indices, const float* values, const float* x, float* y,
                             int row_lo, int row_hi, cudaStream_t stream);
+// ell_gated_kernel.cu
+bool ell_gated_applies(int rows, int width, const int* col_indices, const float* values);
+int ell_gated_windows(int rows);
+int ell_gated_window_rows();
+int ell_gated_warps_per_window();
+cudaError_t launch_ell_window_max_col(int rows, int width, const int* col_indices, int* d_wmax, cudaStream_t stream);
+cudaError_t launch_fill_sentinel(float* x, size_t n, cudaStream_t stream);
+cudaError_t launch_ell_gated(int rows, int width, const int* col_indices, const float* values, const float* x, float* y,
+                             const int* d_window_poll, const unsigned* d_done_flag, unsigned epoch, unsigned* abort_word,
+                             unsigned* abort_host, unsigned long long timeout_ns, unsigned poll_sleep_ns, unsigned* d_progress,
+                             const unsigned char* d_window_chunk, const unsigned* d_chunk_warps, unsigned* ready_host,
+                             cudaStream_t stream);
 
 namespace {
 
@@ -49,6 +71,27 @@ __global__ void ell_chunk_col_range_kernel(int rows, int width, const int* __res
     if (mine >= 0 && hi >= 0) { atomicMin(cmin + mine, lo); atomicMax(cmax + mine, hi); }
 }
 
+int env_or(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : fallback;
+}
+
+// cuStreamWriteValue32: a stream-ordered 32-bit store executed by the stream's front
+// end (no SM, no copy descriptor) -- looked up at run time like every driver entry point of this library (symm.cpp)
+using StreamValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamValue32Fn driver_entry(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        p = nullptr;
+    }
+    return reinterpret_cast<StreamValue32Fn>(p);
+}
+StreamValue32Fn write_value32() {
+    static const StreamValue32Fn fn = driver_entry("cuStreamWriteValue32");
+    return fn;
+}
 }  // namespace
 
 struct EllHostPlan {
@@ -66,7 +109,32 @@ struct EllHostPlan {
     cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
     std::vector<cudaEvent_t> ev_x, ev_y;
     cudaEvent_t ev_start = nullptr;
+    // gated form
+    bool gated = false;
+    int g_chunks = 0;                 // row chunks of the download
+    std::vector<int> g_first;         // [g_chunks + 1] first 256-row window of every chunk
+    unsigned char* d_window_chunk = nullptr;  // per window: its chunk
+    unsigned* d_chunk_warps = nullptr;        // per chunk: consumer warps that report
+    size_t up_lo = 0, up_hi = 0;      // x entries [up_lo, up_hi) travel (what some row reads, at x_chunk granularity)
+    int* d_poll = nullptr;            // per window: the largest column it reads
+    unsigned* d_done = nullptr;       // epoch of the call whose upload is complete
+    unsigned* d_progress = nullptr;   // [g_chunks] consumer warps done in the current call
+    unsigned* h_ready = nullptr;      // [g_chunks] epoch of the call whose chunk is complete (mapped, page-locked: the kernel writes it)
+    unsigned* h_ready_dev = nullptr;  // its device address
+    unsigned* d_abort = nullptr;      // device word: a producer timed out
+    unsigned* h_abort = nullptr;      // the same for the host (mapped, page-locked)
+    unsigned* h_abort_dev = nullptr;  // its device address
+    unsigned epoch = 0;
+    cudaStream_t s_down2 = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_fill = nullptr;
     ~EllHostPlan() {
+        if (s_run) cudaStreamSynchronize(s_run);  // the sentinel refill of the last call may still be running
+        cudaFree(d_poll); cudaFree(d_done); cudaFree(d_progress); cudaFree(d_abort); cudaFree(d_window_chunk); cudaFree(d_chunk_warps);
+        if (h_abort) cudaFreeHost(h_abort);
+        if (h_ready) cudaFreeHost(h_ready);
+        if (s_down2) cudaStreamDestroy(s_down2);
+        if (ev_up) cudaEventDestroy(ev_up);
+        if (ev_fill) cudaEventDestroy(ev_fill);
         for (auto e : ev_x) cudaEventDestroy(e);
         for (auto e : ev_y) cudaEventDestroy(e);
         if (ev_start) cudaEventDestroy(ev_start);
@@ -137,6 +205,64 @@ int ell_host_plan_create(const ELLMatrix* A, int chunks, EllHostPlan** out) {
         cudaFree(d_min);
         cudaFree(d_max);
     }
+    // gated form: per-window poll table, completion flag, progress counters, abort words, second download stream
+    if (ok && p->ranged && env_or("SPMV_B200_HOST_GATED", 1) && write_value32() &&
+        ell_gated_applies(p->rows, p->width, p->d_cols, p->d_vals)) {
+        const int windows = ell_gated_windows(p->rows);
+        // Download chunks: equal ones.  Every D2H copy costs ~19 us of idle down-link on B200 (its completion is a PCIe
+        // round trip under load) and the download trails the product by one chunk: 6 / 8 / 10 / 12 chunks -> 1.663 /
+        // 1.640 / 1.669 / 1.683 ms on config 2; a small first chunk followed by growing ones (the download is the
+        // slower direction) was measured too and loses to 8 equal chunks (1.71-1.96 ms) -- profiles/r2_host_gated.txt
+        {
+            const int want = std::min(255, std::max(1, env_or("SPMV_B200_HOST_GATED_CHUNKS", 8)));
+            const int size = (windows + want - 1) / want;
+            p->g_first.assign(1, 0);
+            while (p->g_first.back() < windows) p->g_first.push_back(std::min(windows, p->g_first.back() + size));
+            p->g_chunks = static_cast<int>(p->g_first.size()) - 1;
+        }
+        int first = 0, last = p->x_chunks - 1;
+        while (first < p->x_chunks && !p->x_needed[first]) ++first;
+        while (last >= first && !p->x_needed[last]) --last;
+        p->up_lo = static_cast<size_t>(first) * p->x_chunk;
+        p->up_hi = last < first ? p->up_lo : std::min<size_t>(static_cast<size_t>(p->cols), static_cast<size_t>(last + 1) * p->x_chunk);
+        bool g = cudaMalloc(&p->d_poll, sizeof(int) * windows) == cudaSuccess &&
+                 cudaMalloc(&p->d_done, sizeof(unsigned)) == cudaSuccess &&
+                 cudaMalloc(&p->d_progress, sizeof(unsigned) * p->g_chunks) == cudaSuccess &&
+                 cudaMalloc(&p->d_window_chunk, windows) == cudaSuccess &&
+                 cudaMalloc(&p->d_chunk_warps, sizeof(unsigned) * p->g_chunks) == cudaSuccess &&
+                 cudaMalloc(&p->d_abort, sizeof(unsigned)) == cudaSuccess &&
+                 cudaHostAlloc(&p->h_abort, sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess &&
+                 cudaHostGetDevicePointer(&p->h_abort_dev, p->h_abort, 0) == cudaSuccess &&
+                 cudaHostAlloc(&p->h_ready, sizeof(unsigned) * p->g_chunks, cudaHostAllocMapped) == cudaSuccess &&
+                 cudaHostGetDevicePointer(&p->h_ready_dev, p->h_ready, 0) == cudaSuccess &&
+                 cudaStreamCreateWithFlags(&p->s_down2, cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p->ev_up, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p->ev_fill, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaMemset(p->d_done, 0, sizeof(unsigned)) == cudaSuccess &&
+                 cudaMemset(p->d_progress, 0, sizeof(unsigned) * p->g_chunks) == cudaSuccess &&
+                 cudaMemset(p->d_abort, 0, sizeof(unsigned)) == cudaSuccess &&
+                 launch_ell_window_max_col(p->rows, p->width, p->d_cols, p->d_poll, nullptr) == cudaSuccess &&
+                 launch_fill_sentinel(p->d_x, static_cast<size_t>(std::max(p->cols, 1)), nullptr) == cudaSuccess &&
+                 cudaEventRecord(p->ev_fill, nullptr) == cudaSuccess &&
+                 cudaDeviceSynchronize() == cudaSuccess;
+        if (g) {
+            std::vector<unsigned char> wc(windows);
+            std::vector<unsigned> cw(p->g_chunks);
+            for (int c = 0; c < p->g_chunks; ++c) {
+                cw[c] = static_cast<unsigned>(p->g_first[c + 1] - p->g_first[c]) * static_cast<unsigned>(ell_gated_warps_per_window());
+                for (int w = p->g_first[c]; w < p->g_first[c + 1]; ++w) wc[w] = static_cast<unsigned char>(c);
+            }
+            g = cudaMemcpy(p->d_window_chunk, wc.data(), windows, cudaMemcpyHostToDevice) == cudaSuccess &&
+                cudaMemcpy(p->d_chunk_warps, cw.data(), sizeof(unsigned) * p->g_chunks, cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+        if (g) {
+            *p->h_abort = 0;
+            for (int c = 0; c < p->g_chunks; ++c) p->h_ready[c] = 0;
+        } else {
+            cudaGetLastError();
+        }
+        p->gated = g;
+    }
     if (!ok) {
         cudaGetLastError();
         delete p;
@@ -148,6 +274,84 @@ int ell_host_plan_create(const ELLMatrix* A, int chunks, EllHostPlan** out) {
 
 void ell_host_plan_destroy(EllHostPlan* p) { delete p; }
 
+namespace {
+
+// The gated form.  0: y is complete; 1: the kernel gave up waiting (nothing usable in y: the caller runs the
+// chunked form and stops using this one); < 0: CUDA error.
+int run_gated(EllHostPlan* p, const float* x_host, float* y_host) {
+    static const int down_streams = std::min(2, std::max(1, env_or("SPMV_B200_HOST_DOWN_STREAMS", 1)));
+    static const unsigned long long timeout_ns = 1000000ull * static_cast<unsigned long long>(std::max(1, env_or("SPMV_B200_HOST_GATED_TIMEOUT_MS", 2000)));
+    static const unsigned poll_sleep_ns = static_cast<unsigned>(std::max(0, env_or("SPMV_B200_HOST_GATED_POLL_NS", 200)));
+    static const bool trace = getenv("SPMV_B200_TRACE") != nullptr;
+    const StreamValue32Fn write32 = write_value32();
+    const unsigned epoch = ++p->epoch == 0 ? ++p->epoch : p->epoch;  // flags start at 0: never a valid epoch
+    cudaStream_t downs[2] = {p->s_down, down_streams > 1 ? p->s_down2 : p->s_down};
+    const int rows_per_window = ell_gated_window_rows();
+    const int windows = ell_gated_windows(p->rows);
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since_begin_us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
+    bool ok = true;
+    // order after whatever the caller queued on the legacy stream (matrix upload, ...)
+    ok = ok && cudaEventRecord(p->ev_start, nullptr) == cudaSuccess;
+    for (cudaStream_t s : {p->s_up, p->s_run, p->s_down, p->s_down2}) ok = ok && cudaStreamWaitEvent(s, p->ev_start, 0) == cudaSuccess;
+    // up: one copy over the sentinels (which the previous call re-laid after its product), then the completion flag
+    ok = ok && cudaStreamWaitEvent(p->s_up, p->ev_fill, 0) == cudaSuccess;
+    if (ok && p->up_hi > p->up_lo)
+        ok = cudaMemcpyAsync(p->d_x + p->up_lo, x_host + p->up_lo, (p->up_hi - p->up_lo) * sizeof(float), cudaMemcpyHostToDevice, p->s_up) == cudaSuccess;
+    ok = ok && write32(reinterpret_cast<CUstream>(p->s_up), reinterpret_cast<CUdeviceptr>(p->d_done), epoch, 0) == CUDA_SUCCESS;
+    ok = ok && cudaEventRecord(p->ev_up, p->s_up) == cudaSuccess;
+    if (!ok) return -1;
+    // the product, consuming x as it lands; then (once the upload is over, too) the sentinels for the next call
+    ok = cudaMemsetAsync(p->d_progress, 0, sizeof(unsigned) * p->g_chunks, p->s_run) == cudaSuccess &&
+         launch_ell_gated(p->rows, p->width, p->d_cols, p->d_vals, p->d_x, p->d_y, p->d_poll, p->d_done, epoch, p->d_abort,
+                          p->h_abort_dev, timeout_ns, poll_sleep_ns, p->d_progress, p->d_window_chunk, p->d_chunk_warps, p->h_ready_dev, p->s_run) == cudaSuccess;
+    const bool launched = ok;
+    ok = ok && cudaStreamWaitEvent(p->s_run, p->ev_up, 0) == cudaSuccess;
+    ok = ok && launch_fill_sentinel(p->d_x + p->up_lo, p->up_hi - p->up_lo, p->s_run) == cudaSuccess;
+    ok = ok && cudaEventRecord(p->ev_fill, p->s_run) == cudaSuccess;
+    const double t_queued = since_begin_us();
+    // down: this thread watches the ready words the kernel writes and queues the copy of a chunk the moment it is complete
+    std::vector<double> t_ready(trace ? p->g_chunks : 0);
+    for (int c = 0; launched && ok && c < p->g_chunks; ++c) {
+        volatile unsigned* ready = p->h_ready + c;
+        unsigned spins = 0;
+        while (*ready != epoch) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            if ((++spins & 0x3fffu) == 0) {  // a failed kernel must not leave this thread spinning
+                const cudaError_t q = cudaStreamQuery(p->s_run);
+                if ((q != cudaSuccess && q != cudaErrorNotReady) || since_begin_us() > 30e6) { ok = false; break; }
+                if (q == cudaSuccess && *ready != epoch) { ok = false; break; }
+            }
+        }
+        if (!ok) break;
+        if (trace) t_ready[c] = since_begin_us();
+        const int w_lo = p->g_first[c], w_hi = p->g_first[c + 1];
+        const size_t lo = static_cast<size_t>(w_lo) * rows_per_window;
+        const size_t hi = std::min<size_t>(static_cast<size_t>(p->rows), static_cast<size_t>(w_hi) * rows_per_window);
+        ok = cudaMemcpyAsync(y_host + lo, p->d_y + lo, (hi - lo) * sizeof(float), cudaMemcpyDeviceToHost, downs[c & 1]) == cudaSuccess;
+    }
+    ok = cudaStreamSynchronize(p->s_down) == cudaSuccess && ok;
+    ok = cudaStreamSynchronize(p->s_down2) == cudaSuccess && ok;
+    ok = cudaStreamSynchronize(p->s_up) == cudaSuccess && ok;
+    if (trace) {
+        fprintf(stderr, "[gated] queued %.0f us; chunk ready at [us]:", t_queued);
+        for (double t : t_ready) fprintf(stderr, " %.0f", t);
+        fprintf(stderr, "; done %.0f us\n", since_begin_us());
+    }
+    if (!ok) return -1;
+    if (*static_cast<volatile unsigned*>(p->h_abort) != 0) {
+        cudaStreamSynchronize(p->s_run);
+        *p->h_abort = 0;
+        cudaMemset(p->d_abort, 0, sizeof(unsigned));
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
 // Blocking: returns when y_host is complete.  x_host / y_host should be page-locked (cudaHostAlloc /
 // cudaHostRegister) for the copies to overlap; pageable memory works but serialises.
 int spmv_ell_host(EllHostPlan* p, const float* x_host, float* y_host) {
@@ -155,6 +359,15 @@ int spmv_ell_host(EllHostPlan* p, const float* x_host, float* y_host) {
     if (!p || !x_host || !y_host) return static_cast<int>(SpMVError::INVALID_ARGUMENT);
     if (p->rows <= 0) return 0;
     bool ok = true;
+    if (p->gated) {
+        const int rc = run_gated(p, x_host, y_host);
+        if (rc == 0) return 0;
+        cudaGetLastError();
+        for (cudaStream_t s : {p->s_up, p->s_run, p->s_down, p->s_down2}) cudaStreamSynchronize(s);
+        cudaGetLastError();
+        p->gated = false;  // the chunked form from now on
+        if (rc < 0) return static_cast<int>(SpMVError::KERNEL_LAUNCH);
+    }
     // order after whatever the caller queued on the legacy stream (matrix upload, ...)
     ok = ok && cudaEventRecord(p->ev_start, nullptr) == cudaSuccess;
     ok = ok && cudaStreamWaitEvent(p->s_up, p->ev_start, 0) == cudaSuccess;
@@ -213,7 +426,9 @@ int spmv_ell_host(EllHostPlan* p, const float* x_host, float* y_host) {
 // bytes one call moves over PCIe: the x chunks some row reads, and y
 void ell_host_plan_bytes(const EllHostPlan* p, unsigned long long* h2d, unsigned long long* d2h) {
     unsigned long long up = 0;
-    if (p) {
+    if (p && p->gated) {
+        up = sizeof(float) * static_cast<unsigned long long>(p->up_hi - p->up_lo);
+    } else if (p) {
         for (int j = 0; j < p->x_chunks; ++j) {
             if (!p->x_needed[j]) continue;
             const size_t lo = static_cast<size_t>(j) * p->x_chunk;
@@ -222,6 +437,12 @@ void ell_host_plan_bytes(const EllHostPlan* p, unsigned long long* h2d, unsigned
     }
     if (h2d) *h2d = up;
     if (d2h) *d2h = p ? sizeof(float) * static_cast<unsigned long long>(p->rows) : 0;
+}
+
+// whether the next call takes the gated form, and how many row chunks its download uses
+void ell_host_plan_gated(const EllHostPlan* p, int* gated, int* down_chunks) {
+    if (gated) *gated = p && p->gated ? 1 : 0;
+    if (down_chunks) *down_chunks = p && p->gated ? p->g_chunks : 0;
 }
 
 void ell_host_plan_info(const EllHostPlan* p, int* chunks, int* ranged, int* max_lookahead) {

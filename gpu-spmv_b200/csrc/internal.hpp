@@ -296,6 +296,8 @@ void ell_host_plan_destroy(EllHostPlan* plan);
 int spmv_ell_host(EllHostPlan* plan, const float* x_host, float* y_host);
 void ell_host_plan_info(const EllHostPlan* plan, int* chunks, int* ranged, int* max_lookahead);
 void ell_host_plan_bytes(const EllHostPlan* plan, unsigned long long* h2d, unsigned long long* d2h);
+void ell_host_plan_gated(const EllHostPlan* plan, int* gated, int* down_chunks);
+int probe_h2d_order(const float* x_host, size_t n, int samples, long long* out_ns, int mode, unsigned sleep_ns);
 
 // ---- PageRank plan over one row shard (pagerank.cu) -------------------------------------
 struct PrPlan;

@@ -294,7 +294,7 @@ SPMV_B200_API int spmv_b200_spmv_ell_async(const spmv_b200_ell* A, const float* 
  * which x entries every row chunk reads (its column range), so a banded matrix overlaps the PCIe
  * up- and down-link almost completely; any other matrix degenerates to upload, then compute
  * overlapped with the download.  y is bit-identical to spmv_ell.  The matrix's device arrays are
- * borrowed and must outlive the plan.  chunks <= 0: 8.  x_host / y_host should be page-locked. */
+ * borrowed and must outlive the plan.  chunks <= 0: 12.  x_host / y_host should be page-locked. */
 typedef struct spmv_b200_ell_host_plan spmv_b200_ell_host_plan;
 SPMV_B200_API int spmv_b200_ell_host_plan_create(const spmv_b200_ell* A, int chunks,
                                                  spmv_b200_ell_host_plan** out);
@@ -310,6 +310,25 @@ SPMV_B200_API int spmv_b200_ell_host_plan_info(const spmv_b200_ell_host_plan* pl
  * shard of a larger system reads its own band of x), plus all of y */
 SPMV_B200_API int spmv_b200_ell_host_plan_bytes(const spmv_b200_ell_host_plan* plan,
                                                 unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
+
+/* Whether the next call takes the GATED form, and how many row chunks its download uses.  Gated = one
+ * upload copy over a device x pre-filled with a sentinel bit pattern, ONE persistent kernel that consumes x
+ * while it arrives (a window starts when the last x entry it reads is no longer the sentinel; every gather
+ * is checked), and per row chunk one stream-ordered wait + D2H copy queued before the launch and released by
+ * progress counters the kernel advances: no launch boundary, no host thread between upload and download.
+ * SPMV_B200_HOST_GATED=0 selects the chunked form (one upload / launch / download per row chunk); a call
+ * whose x does not arrive within SPMV_B200_HOST_GATED_TIMEOUT_MS repeats itself in the chunked form and the
+ * plan stays there.  An x that really contains the sentinel pattern (0x7FA3C0DE, a signalling NaN) is
+ * handled correctly, only later (such entries are accepted when the upload is complete). */
+SPMV_B200_API int spmv_b200_ell_host_plan_gated(const spmv_b200_ell_host_plan* plan, int* gated, int* down_chunks);
+
+/* Diagnostic behind the gated form's design: the ORDER in which one host-to-device copy of n floats lands in
+ * device memory.  out_ns[i] = arrival time (ns, relative to the earliest) of entry i * (n / samples), observed by
+ * a kernel that polls a sentinel-filled destination while the copy engine writes it (mode 0 / 1 / 2: system-scope /
+ * gpu-scope / volatile loads, sleep_ns between polls; mode < 0: no polling); out_ns[samples] = duration of the copy by
+ * CUDA events, so out_ns holds samples + 1 values.  samples <= 4096. */
+SPMV_B200_API int spmv_b200_probe_h2d_order(const float* x_host, unsigned long long n, int samples, long long* out_ns,
+                                            int mode, unsigned sleep_ns);
 
 /* device-side ELL assembly from the DEVICE arrays of csr (ell_from_csr
  * semantics, src/ell_matrix.cpp:111-159); fills ell's device arrays only

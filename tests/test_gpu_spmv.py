@@ -447,6 +447,55 @@ def test_pipelined_host_buffer_ell(sp, orc, cuda):
     check(30001, 50000, rp.numpy(), ci.numpy(), va.numpy(), 4, False, False)
 
 
+def test_gated_host_buffer_ell(sp, orc, cuda):
+    """The gated form of spmv_b200_spmv_ell_host (one upload, one persistent kernel that consumes x while it
+    arrives, downloads released by progress counters): taken by default for a matrix the TMA ring covers,
+    bit-identical to spmv_cpu_ell over repeated calls (the sentinel refill between calls), with 1 .. many download
+    chunks, with a row count that leaves a partial last window, and with an x that CONTAINS the sentinel bit
+    pattern (accepted once the upload is complete: same bits as the device path spmv_ell)."""
+    import os
+    gen = gen_mod()
+    for grid, chunks in ((512, 24), (510, 7), (256, 1), (1024, 200), (768, 0)):
+        n = grid * grid
+        rp, ci, va = gen.laplacian_2d_csr(grid, "cpu")
+        A = GpuCSR(sp, n, n, rp.numpy(), ci.numpy(), va.numpy())
+        E = sp.ell_create(0, 0, 0)
+        assert sp.ell_from_csr(E, A.mat) == 0 and sp.ell_to_gpu(E) == 0
+        w = E.contents.max_nnz_per_row
+        ec, ev = sp.ell_arrays(E)
+        if chunks:  # that many equal download chunks; 0: the default schedule (small first chunk, growing)
+            os.environ["SPMV_B200_HOST_GATED_CHUNKS"] = str(chunks)
+        plan = C.c_void_p()
+        try:
+            assert sp.lib.spmv_b200_ell_host_plan_create(E, 0, C.byref(plan)) == 0
+        finally:
+            os.environ.pop("SPMV_B200_HOST_GATED_CHUNKS", None)
+        gated, down = C.c_int(), C.c_int()
+        assert sp.lib.spmv_b200_ell_host_plan_gated(plan, C.byref(gated), C.byref(down)) == 0
+        assert gated.value == 1 and 1 <= down.value <= (chunks or 255)
+        yh = torch.empty(n).pin_memory()
+        for seed in (1, 2, 3):
+            x = gen.vector_pm1(n, seed, "cpu").numpy()
+            xh = torch.as_tensor(x).pin_memory()
+            yh.fill_(float("nan"))
+            assert sp.lib.spmv_b200_spmv_ell_host(plan, xh.data_ptr(), yh.data_ptr()) == 0
+            assert np.array_equal(bits(yh.numpy()), bits(orc.spmv_ell(n, w, ec, ev, x))), (grid, chunks, seed)
+        # x holding the sentinel pattern in places (and pageable buffers): same bits as the device path
+        x = gen.vector_pm1(n, 9, "cpu").numpy()
+        x.view(np.uint32)[::1001] = 0x7FA3C0DE
+        x.view(np.uint32)[n - 1] = 0x7FA3C0DE
+        d_x = torch.as_tensor(x).to(cuda)
+        d_y = torch.empty(n, dtype=torch.float32, device=cuda)
+        assert sp.spmv_ell(E, d_x, d_y, None, n).error_code == 0
+        yp = np.full(n, 7.0, np.float32)
+        assert sp.lib.spmv_b200_spmv_ell_host(plan, x.ctypes.data, yp.ctypes.data) == 0
+        assert np.array_equal(bits(yp), bits(d_y.cpu().numpy()))
+        assert sp.lib.spmv_b200_ell_host_plan_gated(plan, C.byref(gated), None) == 0 and gated.value == 1
+        sp.lib.spmv_b200_ell_host_plan_destroy(plan)
+        sp.ell_destroy(E)
+        A.close()
+
+
 def test_benchmark_csr_report_has_roofline_fields(sp, cuda):
     """spmv_b200_benchmark_csr_report: the reference's nine benchmark keys (src/benchmark.cu:187-202) in the
     reference's format, followed by the roofline figures (algorithmic bytes of src/bandwidth.cpp:34-42,
