@@ -76,6 +76,18 @@ int env_or(const char* name, int fallback) {
     return v ? atoi(v) : fallback;
 }
 
+// the device address of a page-locked, device-mapped host buffer (nullptr: y_host is something else, or
+// SPMV_B200_HOST_ZERO_COPY_Y=0)
+float* mapped_device_pointer(float* y_host) {
+    static const int zero_copy = env_or("SPMV_B200_HOST_ZERO_COPY_Y", 1);
+    if (!zero_copy) return nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, y_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        return static_cast<float*>(attr.devicePointer);
+    cudaGetLastError();
+    return nullptr;
+}
+
 // cuStreamWriteValue32: a stream-ordered 32-bit store executed by the stream's front
 // end (no SM, no copy descriptor) -- looked up at run time like every driver entry point of this library (symm.cpp)
 using StreamValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
@@ -126,7 +138,7 @@ struct EllHostPlan {
     unsigned* h_abort_dev = nullptr;  // its device address
     unsigned epoch = 0;
     cudaStream_t s_down2 = nullptr;
-    cudaEvent_t ev_up = nullptr, ev_fill = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_fill = nullptr, ev_kernel = nullptr;
     ~EllHostPlan() {
         if (s_run) cudaStreamSynchronize(s_run);  // the sentinel refill of the last call may still be running
         cudaFree(d_poll); cudaFree(d_done); cudaFree(d_progress); cudaFree(d_abort); cudaFree(d_window_chunk); cudaFree(d_chunk_warps);
@@ -135,6 +147,7 @@ struct EllHostPlan {
         if (s_down2) cudaStreamDestroy(s_down2);
         if (ev_up) cudaEventDestroy(ev_up);
         if (ev_fill) cudaEventDestroy(ev_fill);
+        if (ev_kernel) cudaEventDestroy(ev_kernel);
         for (auto e : ev_x) cudaEventDestroy(e);
         for (auto e : ev_y) cudaEventDestroy(e);
         if (ev_start) cudaEventDestroy(ev_start);
@@ -238,6 +251,7 @@ int ell_host_plan_create(const ELLMatrix* A, int chunks, EllHostPlan** out) {
                  cudaStreamCreateWithFlags(&p->s_down2, cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&p->ev_up, cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&p->ev_fill, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p->ev_kernel, cudaEventDisableTiming) == cudaSuccess &&
                  cudaMemset(p->d_done, 0, sizeof(unsigned)) == cudaSuccess &&
                  cudaMemset(p->d_progress, 0, sizeof(unsigned) * p->g_chunks) == cudaSuccess &&
                  cudaMemset(p->d_abort, 0, sizeof(unsigned)) == cudaSuccess &&
@@ -302,9 +316,16 @@ int run_gated(EllHostPlan* p, const float* x_host, float* y_host) {
     ok = ok && cudaEventRecord(p->ev_up, p->s_up) == cudaSuccess;
     if (!ok) return -1;
     // the product, consuming x as it lands; then (once the upload is over, too) the sentinels for the next call
-    ok = cudaMemsetAsync(p->d_progress, 0, sizeof(unsigned) * p->g_chunks, p->s_run) == cudaSuccess &&
-         launch_ell_gated(p->rows, p->width, p->d_cols, p->d_vals, p->d_x, p->d_y, p->d_poll, p->d_done, epoch, p->d_abort,
-                          p->h_abort_dev, timeout_ns, poll_sleep_ns, p->d_progress, p->d_window_chunk, p->d_chunk_warps, p->h_ready_dev, p->s_run) == cudaSuccess;
+    // y in page-locked, device-mapped host memory (cudaHostAlloc / cudaHostRegister: what a pinned buffer is under UVA):
+    // the kernel stores its rows STRAIGHT into y_host -- 128-byte posted PCIe writes that leave as the rows are
+    // finished, in step with the upload: 1.47 ms on config 2 against 1.64 ms with 8 D2H copies (each copy costs ~19 us
+    // of idle link), profiles/r2_host_gated.txt.  Any other y_host goes down in D2H chunks.
+    float* y_direct = mapped_device_pointer(y_host);
+    ok = (y_direct || cudaMemsetAsync(p->d_progress, 0, sizeof(unsigned) * p->g_chunks, p->s_run) == cudaSuccess) &&
+         launch_ell_gated(p->rows, p->width, p->d_cols, p->d_vals, p->d_x, y_direct ? y_direct : p->d_y, p->d_poll, p->d_done, epoch, p->d_abort,
+                          p->h_abort_dev, timeout_ns, poll_sleep_ns, y_direct ? nullptr : p->d_progress, p->d_window_chunk, p->d_chunk_warps,
+                          p->h_ready_dev, p->s_run) == cudaSuccess &&
+         cudaEventRecord(p->ev_kernel, p->s_run) == cudaSuccess;
     const bool launched = ok;
     ok = ok && cudaStreamWaitEvent(p->s_run, p->ev_up, 0) == cudaSuccess;
     ok = ok && launch_fill_sentinel(p->d_x + p->up_lo, p->up_hi - p->up_lo, p->s_run) == cudaSuccess;
@@ -312,7 +333,7 @@ int run_gated(EllHostPlan* p, const float* x_host, float* y_host) {
     const double t_queued = since_begin_us();
     // down: this thread watches the ready words the kernel writes and queues the copy of a chunk the moment it is complete
     std::vector<double> t_ready(trace ? p->g_chunks : 0);
-    for (int c = 0; launched && ok && c < p->g_chunks; ++c) {
+    for (int c = 0; launched && ok && !y_direct && c < p->g_chunks; ++c) {
         volatile unsigned* ready = p->h_ready + c;
         unsigned spins = 0;
         while (*ready != epoch) {
@@ -332,6 +353,7 @@ int run_gated(EllHostPlan* p, const float* x_host, float* y_host) {
         const size_t hi = std::min<size_t>(static_cast<size_t>(p->rows), static_cast<size_t>(w_hi) * rows_per_window);
         ok = cudaMemcpyAsync(y_host + lo, p->d_y + lo, (hi - lo) * sizeof(float), cudaMemcpyDeviceToHost, downs[c & 1]) == cudaSuccess;
     }
+    if (y_direct && launched) ok = cudaEventSynchronize(p->ev_kernel) == cudaSuccess && ok;  // the kernel's own stores are the download
     ok = cudaStreamSynchronize(p->s_down) == cudaSuccess && ok;
     ok = cudaStreamSynchronize(p->s_down2) == cudaSuccess && ok;
     ok = cudaStreamSynchronize(p->s_up) == cudaSuccess && ok;
@@ -388,15 +410,7 @@ int spmv_ell_host(EllHostPlan* p, const float* x_host, float* y_host) {
         // y in page-locked, device-mapped host memory (cudaHostAlloc / cudaHostRegister: what a pinned buffer is
         // under UVA): the kernel stores its rows STRAIGHT into y_host over PCIe -- the download is the kernel's
         // own posted writes, overlapped row by row with the product, no staging buffer, no per-chunk copy.
-        float* y_direct = nullptr;
-        static const int zero_copy = [] { const char* v = getenv("SPMV_B200_HOST_ZERO_COPY_Y"); return v ? atoi(v) : 1; }();
-        if (zero_copy) {
-            cudaPointerAttributes attr;
-            if (cudaPointerGetAttributes(&attr, y_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
-                y_direct = static_cast<float*>(attr.devicePointer);
-            else
-                cudaGetLastError();
-        }
+        float* y_direct = mapped_device_pointer(y_host);
         int waited = -1;  // highest x chunk the compute stream already waits for
         for (int c = 0; ok && c < p->chunks; ++c) {
             const int lo = c * p->chunk_rows, hi = std::min(p->rows, lo + p->chunk_rows);

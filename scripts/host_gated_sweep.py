@@ -67,16 +67,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
 
 G = "SPMV_B200_HOST_GATED"
 sets = [
-    ("chunked (GATED=0)", {G: "0", "SWEEP_CHUNKS": "12"}),
-    ("gated, equal chunks", {"SWEEP_CHUNKS": "6,8,10,12"}),
-    ("gated, lead 1/64, growth 20 %", {"SWEEP_CHUNKS": "0"}),
-    ("gated, lead 1/64, growth 10 %", {G + "_GROWTH_PCT": "10", "SWEEP_CHUNKS": "0"}),
-    ("gated, lead 1/64, growth 30 %", {G + "_GROWTH_PCT": "30", "SWEEP_CHUNKS": "0"}),
-    ("gated, lead 1/64, growth 50 %", {G + "_GROWTH_PCT": "50", "SWEEP_CHUNKS": "0"}),
-    ("gated, lead 1/32, growth 20 %", {G + "_LEAD_DIV": "32", "SWEEP_CHUNKS": "0"}),
-    ("gated, lead 1/32, growth 35 %", {G + "_LEAD_DIV": "32", G + "_GROWTH_PCT": "35", "SWEEP_CHUNKS": "0"}),
-    ("gated, lead 1/128, growth 20 %", {G + "_LEAD_DIV": "128", "SWEEP_CHUNKS": "0"}),
-    ("gated, lead 1/128, growth 35 %", {G + "_LEAD_DIV": "128", G + "_GROWTH_PCT": "35", "SWEEP_CHUNKS": "0"}),
+    ("chunked (GATED=0), y by the kernel", {G: "0", "SWEEP_CHUNKS": "12"}),
+    ("gated, y by the kernel (default)", {"SWEEP_CHUNKS": "0"}),
+    ("gated, y in 8 D2H copies", {"SPMV_B200_HOST_ZERO_COPY_Y": "0", "SWEEP_CHUNKS": "8"}),
+    ("gated, y by the kernel, poll 0", {G + "_POLL_NS": "0", "SWEEP_CHUNKS": "0"}),
     ("gated, launch-blocking", {"CUDA_LAUNCH_BLOCKING": "1", "SWEEP_CHUNKS": "0"}),
 ]
 for tag, env in sets:
