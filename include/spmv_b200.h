@@ -311,15 +311,16 @@ SPMV_B200_API int spmv_b200_ell_host_plan_info(const spmv_b200_ell_host_plan* pl
 SPMV_B200_API int spmv_b200_ell_host_plan_bytes(const spmv_b200_ell_host_plan* plan,
                                                 unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
 
-/* Whether the next call takes the GATED form, and how many row chunks its download uses.  Gated = one
- * upload copy over a device x pre-filled with a sentinel bit pattern, ONE persistent kernel that consumes x
- * while it arrives (a window starts when the last x entry it reads is no longer the sentinel; every gather
- * is checked), and per row chunk one stream-ordered wait + D2H copy queued before the launch and released by
- * progress counters the kernel advances: no launch boundary, no host thread between upload and download.
- * SPMV_B200_HOST_GATED=0 selects the chunked form (one upload / launch / download per row chunk); a call
- * whose x does not arrive within SPMV_B200_HOST_GATED_TIMEOUT_MS repeats itself in the chunked form and the
- * plan stays there.  An x that really contains the sentinel pattern (0x7FA3C0DE, a signalling NaN) is
- * handled correctly, only later (such entries are accepted when the upload is complete). */
+/* Whether the next call takes the GATED form, and how many row chunks a download by copies would use.  Gated =
+ * one upload copy over a device x pre-filled with a sentinel bit pattern and ONE persistent kernel that consumes x
+ * while it arrives (a 256-row window starts when the last x entry it reads is no longer the sentinel; every gather
+ * is checked, so the result never depends on the order in which the copy lands).  With a page-locked (device-
+ * mapped) y_host the kernel stores y straight into it and nothing is copied down; any other y_host is downloaded
+ * in *down_chunks D2H copies, each queued by the calling thread when the kernel reports the chunk complete.
+ * SPMV_B200_HOST_GATED=0 selects the chunked form (one upload / launch per row chunk); a call whose x does not
+ * arrive within SPMV_B200_HOST_GATED_TIMEOUT_MS repeats itself in the chunked form and the plan stays there.
+ * An x that really contains the sentinel pattern (0x7FA3C0DE, a signalling NaN) is handled correctly, only later
+ * (such entries are accepted when the upload is complete). */
 SPMV_B200_API int spmv_b200_ell_host_plan_gated(const spmv_b200_ell_host_plan* plan, int* gated, int* down_chunks);
 
 /* Diagnostic behind the gated form's design: the ORDER in which one host-to-device copy of n floats lands in
