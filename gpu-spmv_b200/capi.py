@@ -139,6 +139,8 @@ PROTOTYPES = {
     "spmv_b200_version": (C.c_char_p, []),
     "spmv_b200_set_l2_fetch_granularity": (C.c_int, [C.c_int]),
     "spmv_b200_get_l2_fetch_granularity": (C.c_int, []),
+    "spmv_b200_l2_persistence_limits": (C.c_int, [C.POINTER(C.c_ulonglong)] * 3),
+    "spmv_b200_set_l2_persistence": (C.c_int, [vp, vp, C.c_ulonglong, C.c_float, C.c_ulonglong]),
     "spmv_b200_launch_count": (C.c_ulonglong, []),
     "spmv_b200_reference_policy": (C.c_int, [CSR_P, CFG_P]),
     "spmv_b200_spmv_csr_async": (C.c_int, [CSR_P, vp, vp, CFG_P, vp]),

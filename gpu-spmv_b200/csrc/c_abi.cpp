@@ -361,6 +361,38 @@ int spmv_b200_set_l2_fetch_granularity(int bytes) {
     }
     return 0;
 }
+int spmv_b200_l2_persistence_limits(unsigned long long* max_set_aside_bytes, unsigned long long* max_window_bytes, unsigned long long* l2_bytes) {
+    int dev = 0, a = 0, b = 0, c = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&a, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&b, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&c, cudaDevAttrL2CacheSize, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return SPMV_B200_KERNEL_LAUNCH;
+    }
+    if (max_set_aside_bytes) *max_set_aside_bytes = static_cast<unsigned long long>(a);
+    if (max_window_bytes) *max_window_bytes = static_cast<unsigned long long>(b);
+    if (l2_bytes) *l2_bytes = static_cast<unsigned long long>(c);
+    return 0;
+}
+int spmv_b200_set_l2_persistence(void* stream, const void* base, unsigned long long bytes, float hit_ratio, unsigned long long set_aside_bytes) {
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(set_aside_bytes)) != cudaSuccess) {
+        cudaGetLastError();
+        return SPMV_B200_KERNEL_LAUNCH;
+    }
+    cudaStreamAttrValue v;
+    std::memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    v.accessPolicyWindow.num_bytes = base ? static_cast<size_t>(bytes) : 0;
+    v.accessPolicyWindow.hitRatio = hit_ratio;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(static_cast<cudaStream_t>(stream), cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) {
+        cudaGetLastError();
+        return SPMV_B200_KERNEL_LAUNCH;
+    }
+    if (!base) cudaCtxResetPersistingL2Cache();
+    return 0;
+}
 int spmv_b200_get_l2_fetch_granularity(void) {
     size_t v = 0;
     if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) != cudaSuccess) {

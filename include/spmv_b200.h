@@ -273,6 +273,14 @@ SPMV_B200_API const char* spmv_b200_version(void);
  * current value or a negative status. */
 SPMV_B200_API int spmv_b200_set_l2_fetch_granularity(int bytes);
 SPMV_B200_API int spmv_b200_get_l2_fetch_granularity(void);
+/* L2 persistence for the x of products whose x does not fit L2 (design probe, profiles/r2_l2_persist.jsonl): reserve
+ * set_aside_bytes of L2 for persisting lines (cudaLimitPersistingL2CacheSize) and give `stream` an access-policy window
+ * over [base, base + bytes): a hit_ratio share of its lines persists, the rest streams.  base == NULL removes the window
+ * and resets the persisting lines.  limits: the device's maximum set-aside, maximum window and L2 size. */
+SPMV_B200_API int spmv_b200_l2_persistence_limits(unsigned long long* max_set_aside_bytes, unsigned long long* max_window_bytes,
+                                                  unsigned long long* l2_bytes);
+SPMV_B200_API int spmv_b200_set_l2_persistence(void* stream, const void* base, unsigned long long bytes, float hit_ratio,
+                                               unsigned long long set_aside_bytes);
 /* number of kernels this library has launched in this process so far */
 SPMV_B200_API unsigned long long spmv_b200_launch_count(void);
 /* the reference's selector decision without the B200 outlier override
