@@ -496,6 +496,51 @@ def test_gated_host_buffer_ell(sp, orc, cuda):
         A.close()
 
 
+def test_h2d_order_probe_and_l2_persistence_hooks(sp, orc, cuda):
+    """The two design probes behind DESIGN 6 / 8 stay runnable: (i) spmv_b200_probe_h2d_order -- one host-to-device copy
+    lands front to back (the premise of the gated host-buffer call; the gated kernel itself never relies on it);
+    (ii) spmv_b200_set_l2_persistence -- a persisting L2 set-aside + access-policy window over x changes no bit of a product."""
+    gen = gen_mod()
+    n, samples = 1 << 22, 16
+    xh = torch.rand(n).pin_memory()
+    out = (C.c_longlong * (samples + 1))()
+    for _ in range(2):  # the first copy from freshly pinned pages is slow
+        assert sp.lib.spmv_b200_probe_h2d_order(xh.data_ptr(), n, samples, out, 1, 0) == 0
+    arrivals = list(out)[:samples]
+    assert min(arrivals) == 0 and out[samples] > 0
+    assert sum(1 for a, b in zip(arrivals, arrivals[1:]) if b >= a) >= samples - 2, arrivals  # in order (a tie or two allowed)
+    assert sp.lib.spmv_b200_probe_h2d_order(None, n, samples, out, 1, 0) != 0
+
+    lim = [C.c_ulonglong() for _ in range(3)]
+    assert sp.lib.spmv_b200_l2_persistence_limits(*[C.byref(v) for v in lim]) == 0
+    max_aside, max_window, l2 = [v.value for v in lim]
+    assert l2 > 0 and max_window > 0
+    rows = 60000
+    rp, ci, va = gen.random_csr(rows, rows, 7, seed=12, device="cpu")
+    x = gen.vector_pm1(rows, 3, "cpu").numpy()
+    A = GpuCSR(sp, rows, rows, rp.numpy(), ci.numpy(), va.numpy())
+    d_x = torch.as_tensor(x).to(cuda)
+    d_y = torch.empty(rows, dtype=torch.float32, device=cuda)
+    stream = torch.cuda.Stream()
+    cfg = sp.make_config(sp.MERGE_PATH)
+    ys = []
+    for window in (False, True, False):
+        if window:
+            assert sp.lib.spmv_b200_set_l2_persistence(C.c_void_p(stream.cuda_stream), C.c_void_p(d_x.data_ptr()), min(rows * 4, max_window),
+                                                       1.0, min(max_aside, 8 << 20)) == 0
+        else:
+            assert sp.lib.spmv_b200_set_l2_persistence(C.c_void_p(stream.cuda_stream), None, 0, 0.0, 0) == 0
+        d_y.fill_(float("nan"))
+        torch.cuda.synchronize()
+        assert sp.lib.spmv_b200_spmv_csr_async(A.mat, sp.dptr(d_x), sp.dptr(d_y), C.byref(cfg), C.c_void_p(stream.cuda_stream)) == 0
+        stream.synchronize()
+        ys.append(d_y.cpu().numpy().copy())
+    assert np.array_equal(bits(ys[0]), bits(ys[1])) and np.array_equal(bits(ys[0]), bits(ys[2]))
+    y64, scale = orc.spmv_csr_f64(rows, A.rp, A.ci, A.va, x)
+    assert np.all(np.abs(ys[1].astype(np.float64) - y64) <= 1e-5 * scale + 1e-30)
+    A.close()
+
+
 def test_benchmark_csr_report_has_roofline_fields(sp, cuda):
     """spmv_b200_benchmark_csr_report: the reference's nine benchmark keys (src/benchmark.cu:187-202) in the
     reference's format, followed by the roofline figures (algorithmic bytes of src/bandwidth.cpp:34-42,
