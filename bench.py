@@ -410,7 +410,7 @@ def run_product_arm(args):
         assert rc == 0
 
     def wall_time(fn, steps):
-        for _ in range(2):
+        for _ in range(max(3, args.warmup)):  # untimed: the first copies out of freshly pinned pages are slow
             fn()
         if dist_on:
             dist.barrier()
