@@ -52,23 +52,31 @@ cudaError_t launch_ell_gated(int rows, int width, const int* col_indices, const 
 
 namespace {
 
-// min / max column (padding excluded) of every row chunk; chunk c = rows [c * chunk_rows, ...)
+// min / max column (padding excluded) of every row chunk; chunk c = rows [c * chunk_rows, ...).  A block owns a
+// contiguous run of rows (32-bit indexing, coalesced slices), reduces per chunk it touches and issues one atomic pair.
 __global__ void ell_chunk_col_range_kernel(int rows, int width, const int* __restrict__ col_indices, int chunk_rows,
                                            int* __restrict__ cmin, int* __restrict__ cmax) {
-    const long long total = static_cast<long long>(rows) * width;
-    int lo = INT_MAX, hi = -1, mine = -1;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int row = static_cast<int>(i % rows);
-        const int chunk = row / chunk_rows;
-        if (chunk != mine) {
-            if (mine >= 0 && hi >= 0) { atomicMin(cmin + mine, lo); atomicMax(cmax + mine, hi); }
-            mine = chunk; lo = INT_MAX; hi = -1;
+    const int per_block = (rows + gridDim.x - 1) / gridDim.x;
+    const int r_begin = min(rows, static_cast<int>(blockIdx.x) * per_block), r_end = min(rows, r_begin + per_block);
+    __shared__ int s_lo[8], s_hi[8];
+    for (int c = r_begin / chunk_rows; c * static_cast<long long>(chunk_rows) < r_end; ++c) {  // the chunks this block touches
+        const int lo_row = max(r_begin, c * chunk_rows), hi_row = static_cast<int>(min(static_cast<long long>(r_end), (c + 1LL) * chunk_rows));
+        int lo = INT_MAX, hi = -1;
+        for (int row = lo_row + threadIdx.x; row < hi_row; row += blockDim.x)
+            for (int k = 0; k < width; ++k) {
+                const int v = col_indices[static_cast<size_t>(k) * rows + row];
+                if (v >= 0) { lo = min(lo, v); hi = max(hi, v); }
+            }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); }
+            if (hi >= 0) { atomicMin(cmin + c, lo); atomicMax(cmax + c, hi); }
         }
-        const int c = col_indices[i];
-        if (c >= 0) { lo = min(lo, c); hi = max(hi, c); }
+        __syncthreads();
     }
-    if (mine >= 0 && hi >= 0) { atomicMin(cmin + mine, lo); atomicMax(cmax + mine, hi); }
 }
 
 int env_or(const char* name, int fallback) {
