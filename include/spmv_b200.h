@@ -294,15 +294,18 @@ SPMV_B200_API int spmv_b200_spmv_csr_async(const spmv_b200_csr* A, const float* 
 SPMV_B200_API int spmv_b200_spmv_ell_async(const spmv_b200_ell* A, const float* d_x, float* d_y,
                                            void* stream);
 
-/* ---- host-buffer SpMV, pipelined ------------------------------------------
+/* ---- host-buffer SpMV, overlapped -----------------------------------------
  * y_host = A x_host for an ELL matrix resident on the device while x and y live in HOST memory:
  * what a caller of the reference writes as cudaMemcpy(x) + spmv_ell + cudaMemcpy(y)
  * (reference README.md:98-118, src/benchmark.cu:36-38,95-102), with the upload of x, the product
- * and the download of y pipelined over row chunks on three streams.  The plan measures, once,
- * which x entries every row chunk reads (its column range), so a banded matrix overlaps the PCIe
- * up- and down-link almost completely; any other matrix degenerates to upload, then compute
- * overlapped with the download.  y is bit-identical to spmv_ell.  The matrix's device arrays are
- * borrowed and must outlive the plan.  chunks <= 0: 12.  x_host / y_host should be page-locked. */
+ * and the way down of y overlapped.  Two forms (spmv_b200_ell_host_plan_gated below tells which):
+ * the GATED form -- one upload, one persistent kernel that consumes x while it arrives; the default
+ * for matrices the TMA ring covers -- and the CHUNKED form -- upload, product and download pipelined
+ * over `chunks` row chunks on three streams; the plan measures, once, which x entries every row chunk
+ * reads (its column range), so a banded matrix overlaps the PCIe up- and down-link, any other matrix
+ * degenerates to upload, then compute overlapped with the download.  y is bit-identical to spmv_ell
+ * in both.  The matrix's device arrays are borrowed and must outlive the plan.  chunks <= 0: 12.
+ * x_host / y_host should be page-locked (with a page-locked y_host the kernels store y straight into it). */
 typedef struct spmv_b200_ell_host_plan spmv_b200_ell_host_plan;
 SPMV_B200_API int spmv_b200_ell_host_plan_create(const spmv_b200_ell* A, int chunks,
                                                  spmv_b200_ell_host_plan** out);
