@@ -151,6 +151,63 @@ int pr_plan_hub_columns(const PrPlan* p) {
 }
 double* pr_plan_tmp(PrPlan* p) { return p->tmp; }
 
+// pagerank_small.cu
+bool pagerank_small_applies(int n, int nnz);
+cudaError_t pagerank_small_run(const CsrView& A, float damping, float tolerance, int max_iterations, const uint32_t* d_bits,
+                               float* buf_a, float* buf_b, const float* d_dsum, float* l2_history, int history_capacity,
+                               int* iterations, float* residual, double* l1, bool* converged, int* final_buffer,
+                               cudaStream_t stream);
+
+// The loop of a small graph in one persistent kernel (pagerank_small.cu); same set-up, same outputs as the
+// multi-kernel loop below.  kNotHandled: take that loop instead.
+constexpr int kNotHandled = 1 << 20;
+static int pagerank_device_small(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,
+                                 float* final_residual, bool* converged, double* l1_residual, bool normalize, float* l2_history,
+                                 int history_capacity) {
+    const int n = adj->num_rows;
+    if (!adj->d_row_ptrs || (adj->nnz > 0 && (!adj->d_col_indices || !adj->d_values))) return kNotHandled;  // the loop below reports it
+    const CsrView A = view_of(adj);
+    cudaStream_t stream = nullptr;
+    const size_t words = (static_cast<size_t>(n) + 31) / 32;
+    float *d_a = nullptr, *d_b = nullptr, *d_dsum = nullptr;
+    double *d_colsum = nullptr, *d_tmp = nullptr;
+    uint32_t* d_bits = nullptr;
+    const bool ok = cudaMalloc(&d_a, sizeof(float) * n) == cudaSuccess && cudaMalloc(&d_b, sizeof(float) * n) == cudaSuccess &&
+                    cudaMalloc(&d_colsum, sizeof(double) * n) == cudaSuccess && cudaMalloc(&d_bits, sizeof(uint32_t) * words) == cudaSuccess &&
+                    cudaMalloc(&d_dsum, sizeof(float)) == cudaSuccess && cudaMalloc(&d_tmp, sizeof(double) * kTmpDoubles) == cudaSuccess;
+    int rc = 0;
+    if (!ok) {
+        cudaGetLastError();
+        rc = static_cast<int>(SpMVError::CUDA_MALLOC);
+    } else {
+        // dangling nodes, r = 1/n and its dangling mass: exactly as below
+        cudaMemsetAsync(d_colsum, 0, sizeof(double) * n, stream);
+        launch_colsum(A, d_colsum, stream);
+        launch_dangling_bits(d_colsum, n, n, d_bits, stream);
+        launch_pr_init(n, d_bits, d_a, d_dsum, d_tmp, stream);
+        int fin = 0;
+        const cudaError_t e = pagerank_small_run(A, config->damping_factor, config->tolerance, config->max_iterations, d_bits, d_a, d_b,
+                                                 d_dsum, l2_history, history_capacity, iterations, final_residual, l1_residual,
+                                                 converged, &fin, stream);
+        if (e == cudaErrorNotSupported) {
+            rc = kNotHandled;
+        } else if (e != cudaSuccess) {
+            cudaGetLastError();
+            rc = static_cast<int>(SpMVError::KERNEL_LAUNCH);
+        } else {
+            const float* vec = fin ? d_b : d_a;
+            if (normalize) launch_normalize(vec, n, d_ranks, d_tmp, stream);
+            else cudaMemcpyAsync(d_ranks, vec, sizeof(float) * n, cudaMemcpyDeviceToDevice, stream);
+            if (cudaStreamSynchronize(stream) != cudaSuccess) {
+                cudaGetLastError();
+                rc = static_cast<int>(SpMVError::KERNEL_LAUNCH);
+            }
+        }
+    }
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_colsum); cudaFree(d_bits); cudaFree(d_dsum); cudaFree(d_tmp);
+    return rc;
+}
+
 // The whole loop on one device; d_ranks receives the ranks, normalised on the device with an
 // f64 sum when `normalize` is set, else the raw final iterate.
 int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d_ranks, int* iterations,
@@ -169,6 +226,12 @@ int pagerank_device(const CSRMatrix* adj, const PageRankConfig* config, float* d
     // non-square adjacency: the reference's first spmv_csr(adj, ..., vec_size = n) fails with INVALID_DIMENSION and
     // pagerank() returns the uniform vector with iterations = 0 (src/pagerank.cu:102-107); pagerank() below does the same
     if (adj->num_cols != n) return static_cast<int>(SpMVError::INVALID_DIMENSION);
+
+    if (pagerank_small_applies(n, adj->nnz)) {  // launch-bound sizes: the whole loop in one persistent kernel
+        const int r = pagerank_device_small(adj, config, d_ranks, iterations, final_residual, converged, l1_residual, normalize,
+                                            l2_history, history_capacity);
+        if (r != kNotHandled) return r;
+    }
 
     cudaStream_t stream = nullptr;
     PrPlan* plan = nullptr;

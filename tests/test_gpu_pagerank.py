@@ -2,6 +2,7 @@
 (src/pagerank.cu:50-153) through the C ABI.  north_star: rank vectors within
 an L1 distance of 1e-6, identical top-k up to ties."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -279,3 +280,41 @@ def test_non_square_adjacency_is_rejected(sp, ref, cuda):
     it_ref = ref.L.ref_pagerank(h, 0.85, 1e-6, 50, r_ref.ctypes.data_as(C.POINTER(C.c_float)), C.byref(r_res), C.byref(r_conv))
     assert it_ref == 0 and not r_conv.value and np.array_equal(r_ref, ranks)
     sp.csr_destroy(G)
+
+
+def test_one_kernel_loop_for_small_graphs(sp, orc, cuda):
+    """pagerank_small.cu: graphs of launch-bound size run the whole loop in one persistent cooperative kernel (grid
+    barrier per iteration, stop rule on the device).  Same contract as the multi-kernel loop: within L1 1e-6 of the f64
+    restatement at the same iteration count, the reference's stop rule (converged at the iteration the oracle converges,
+    +-1 for a residual at the tolerance), residual history, max_iterations = 0 returns the initial vector; and the two
+    loops agree with each other (child processes: the switch is read once per process)."""
+    import subprocess
+    import sys
+    gen = gen_mod()
+    for scale, ef, seed in ((6, 4, 3), (11, 16, 4), (15, 8, 5)):
+        n, rp, ci, va = gen.rmat_pagerank_csr(scale, ef, seed, "cpu")
+        rp_n, ci_n, va_n = rp.numpy(), ci.numpy(), va.numpy()
+        G = sp.csr_from_arrays(n, n, rp_n, ci_n, va_n)
+        assert sp.csr_to_gpu(G) == 0
+        d_ranks = torch.empty(n, dtype=torch.float32, device=cuda)
+        rc, iters, res, conv, l1 = sp.pagerank_device(G, d_ranks, sp.make_pagerank_config(0.85, 1e-6, 100))
+        assert rc == 0 and conv and 1 <= iters <= 100 and res < 1e-6
+        o_ranks, o_it, o_l2, o_l1, o_conv = orc.pagerank_f64(n, n, rp_n, ci_n, va_n, 0.85, 1e-6, 100, fixed_it=iters)
+        assert np.abs(d_ranks.cpu().numpy().astype(np.float64) - o_ranks).sum() <= 1e-6, scale
+        free_it = orc.pagerank_f64(n, n, rp_n, ci_n, va_n, 0.85, 1e-6, 100)[1]
+        assert abs(free_it - iters) <= 1, (scale, free_it, iters)
+        assert abs(float(d_ranks.double().sum()) - 1.0) <= 1e-5
+        rc, it0, _, conv0, _ = sp.pagerank_device(G, d_ranks, sp.make_pagerank_config(0.85, 1e-6, 0))
+        assert rc == 0 and it0 == 0 and not conv0
+        assert np.allclose(d_ranks.cpu().numpy(), 1.0 / n, rtol=1e-6, atol=0.0)
+        rc, it_h, res_h, conv_h, hist = sp.pagerank_device_history(G, d_ranks, sp.make_pagerank_config(0.85, 1e-6, 100), capacity=100)
+        assert rc == 0 and it_h == iters and conv_h and hist[iters - 1] == np.float32(res_h) and np.all(hist[:iters] > 0)
+        assert np.all(np.isnan(hist[iters:]))
+        sp.csr_destroy(G)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "scripts", "time_small_pagerank.py")], cwd=root, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:]
+    print(p.stdout)
+    dists = [float(ln.split("iterations ")[1].split(",")[0]) for ln in p.stdout.splitlines() if ln.startswith("scale ") and "L1 distance" in ln]
+    assert len(dists) == 7 and max(dists) <= 1e-6, p.stdout[-2000:]
