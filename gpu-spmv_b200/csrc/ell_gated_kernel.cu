@@ -18,14 +18,16 @@
 //     result never depends on the ORDER in which the copy engine writes;
 //   * a stream-ordered 32-bit write after the copy (cuStreamWriteValue32) publishes "all of x is
 //     there": an x entry that REALLY holds the sentinel pattern is accepted then -- correct, only late;
-//   * every consumer warp adds 1 to the progress counter of its row chunk after its rows are stored;
-//     the warp that completes a chunk writes the call's epoch into ready[chunk] in page-locked HOST
-//     memory (one posted PCIe write, ~1 us); the calling thread -- the call is blocking, it has nothing
-//     else to do -- polls those words in order and queues the D2H copy of a chunk the moment it is
-//     ready.  (Stream-ordered waits, cuStreamWaitValue32, were measured first: the front end re-polls a
-//     failed wait so rarely that the download trailed the product by ~50 us PER CHUNK.)
-// A window therefore waits for the 16 KB of x behind it instead of 1/12 of x, and both PCIe
-// directions run as plain DMA.
+//   * y leaves as it is finished.  y_host page-locked (the default case): the row owners store their rows
+//     STRAIGHT into it -- 128-byte posted PCIe writes in step with the upload, no copy call at all (1.42 ms on
+//     config 2; two bare DMA copies with no compute take 1.39 ms).  Any other y_host: every consumer warp adds 1
+//     to the progress counter of its row chunk; the warp that completes a chunk writes the call's epoch into
+//     ready[chunk] in page-locked HOST memory (one posted PCIe write, ~1 us), and the calling thread -- the call
+//     is blocking, it has nothing else to do -- polls those words in order and queues the D2H copy of a chunk
+//     the moment it is ready (1.64 ms: each copy costs ~19 us of idle link).  (Stream-ordered waits,
+//     cuStreamWaitValue32, were measured first: the front end re-polls a failed wait so rarely that the download
+//     trailed the product by ~50 us PER CHUNK.)
+// A window therefore waits for the 16 KB of x behind it instead of 1/12 of x.
 //
 // Safety: a producer that sees neither its entry nor the completion flag within `timeout_ns` (a failed
 // copy) sets *abort_word; everybody stops waiting, the kernel drains with meaningless rows and the
