@@ -318,9 +318,12 @@ int run_gated(EllHostPlan* p, const float* x_host, float* y_host) {
     for (cudaStream_t s : {p->s_up, p->s_run, p->s_down, p->s_down2}) ok = ok && cudaStreamWaitEvent(s, p->ev_start, 0) == cudaSuccess;
     // up: one copy over the sentinels (which the previous call re-laid after its product), then the completion flag
     ok = ok && cudaStreamWaitEvent(p->s_up, p->ev_fill, 0) == cudaSuccess;
-    if (ok && p->up_hi > p->up_lo)
+    // SPMV_B200_HOST_GATED_TEST_STALL=1 (tests only): the upload never happens, so the kernel must time out, drain and hand the
+    // call to the chunked form -- the path that guarantees the call cannot hang
+    static const int test_stall = env_or("SPMV_B200_HOST_GATED_TEST_STALL", 0);
+    if (ok && p->up_hi > p->up_lo && !test_stall)
         ok = cudaMemcpyAsync(p->d_x + p->up_lo, x_host + p->up_lo, (p->up_hi - p->up_lo) * sizeof(float), cudaMemcpyHostToDevice, p->s_up) == cudaSuccess;
-    ok = ok && write32(reinterpret_cast<CUstream>(p->s_up), reinterpret_cast<CUdeviceptr>(p->d_done), epoch, 0) == CUDA_SUCCESS;
+    if (!test_stall) ok = ok && write32(reinterpret_cast<CUstream>(p->s_up), reinterpret_cast<CUdeviceptr>(p->d_done), epoch, 0) == CUDA_SUCCESS;
     ok = ok && cudaEventRecord(p->ev_up, p->s_up) == cudaSuccess;
     if (!ok) return -1;
     // the product, consuming x as it lands; then (once the upload is over, too) the sentinels for the next call

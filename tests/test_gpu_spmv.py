@@ -6,6 +6,7 @@ north_star tolerance |y - y_ref| <= 1e-5 * sum_j |a_ij x_j| per row.
 SCALAR_CSR and ELL keep the reference CPU path's operation order, so they are
 checked BIT-EXACT against it."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -494,6 +495,52 @@ def test_gated_host_buffer_ell(sp, orc, cuda):
         sp.lib.spmv_b200_ell_host_plan_destroy(plan)
         sp.ell_destroy(E)
         A.close()
+
+
+def test_gated_host_call_times_out_into_the_chunked_form(cuda):
+    """The safety net of the gated host-buffer call: if x never arrives (here: the upload is suppressed by a test switch)
+    the kernel's producers time out, everybody drains, and the SAME call repeats itself in the chunked form -- correct y,
+    no hang, and the plan stays chunked afterwards.  Child process: the switches are read once."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import ctypes as C, sys, time, torch
+sys.path.insert(0, %r)
+from _load_pkg import load_pkg
+sp = load_pkg()
+import gpu_spmv_b200.gen as gen
+dev = torch.device("cuda:0")
+grid = 512
+n = grid * grid
+rp, ci, va = gen.laplacian_2d_csr(grid, dev)
+x = gen.vector_pm1(n, 7, dev)
+A = sp.DeviceCSR(n, n, rp, ci, va)
+E = sp.ell_create(0, 0, 0)
+assert sp.ell_from_csr_device(E, A.ptr) == 0
+y = torch.empty(n, device=dev)
+assert sp.spmv_ell(E, x, y, None, n).error_code == 0
+plan = C.c_void_p()
+assert sp.lib.spmv_b200_ell_host_plan_create(E, 0, C.byref(plan)) == 0
+g = C.c_int()
+sp.lib.spmv_b200_ell_host_plan_gated(plan, C.byref(g), None)
+assert g.value == 1
+xh, yh = x.cpu().pin_memory(), torch.full((n,), float("nan")).pin_memory()
+t0 = time.perf_counter()
+assert sp.lib.spmv_b200_spmv_ell_host(plan, xh.data_ptr(), yh.data_ptr()) == 0
+dt = time.perf_counter() - t0
+assert torch.equal(yh.view(torch.int32), y.cpu().view(torch.int32)), "wrong y after the fall-back"
+sp.lib.spmv_b200_ell_host_plan_gated(plan, C.byref(g), None)
+assert g.value == 0, "the plan should stay in the chunked form"
+yh.fill_(float("nan"))
+assert sp.lib.spmv_b200_spmv_ell_host(plan, xh.data_ptr(), yh.data_ptr()) == 0
+assert torch.equal(yh.view(torch.int32), y.cpu().view(torch.int32))
+print("fell back after %%.0f ms" %% (dt * 1e3))
+""" % root
+    env = dict(os.environ, SPMV_B200_HOST_GATED_TEST_STALL="1", SPMV_B200_HOST_GATED_TIMEOUT_MS="40")
+    p = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert p.returncode == 0 and "fell back after" in p.stdout, p.stdout[-3000:]
+    print(p.stdout.strip().splitlines()[-1])
 
 
 def test_h2d_order_probe_and_l2_persistence_hooks(sp, orc, cuda):
