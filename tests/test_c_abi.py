@@ -156,4 +156,18 @@ def test_extension_entry_points_validate_their_arguments(sp):
     assert L.spmv_b200_pr_step_multicast(None, None, None, 0.85, None, None, None, None, 2, 0, None) == bad_arg
     assert L.spmv_b200_pr_plan_set_hot(None, 0, 0, None) == bad_arg
     assert L.spmv_b200_pagerank_device_history(A, None, None, None, None, None, None, -1) == bad_arg
+    # host-buffer call and its probes
+    plan = C.c_void_p()
+    assert L.spmv_b200_ell_host_plan_create(None, 0, C.byref(plan)) == bad_arg and not plan.value
+    E = sp.ell_create(0, 0, 0)
+    assert L.spmv_b200_ell_host_plan_create(E, 0, C.byref(plan)) == bad_fmt  # not on the device
+    sp.ell_destroy(E)
+    assert L.spmv_b200_spmv_ell_host(None, None, None) == bad_arg
+    assert L.spmv_b200_ell_host_plan_gated(None, None, None) == bad_arg
+    assert L.spmv_b200_ell_host_plan_info(None, None, None, None) == bad_arg
+    L.spmv_b200_ell_host_plan_destroy(None)
+    out = (C.c_longlong * 5)()
+    assert L.spmv_b200_probe_h2d_order(None, 1024, 4, out, 0, 0) == bad_arg
+    assert L.spmv_b200_probe_h2d_order(out, 1024, 0, out, 0, 0) == bad_arg
+    assert L.spmv_b200_probe_h2d_order(out, 2, 4, out, 0, 0) == bad_arg
     sp.csr_destroy(A)
